@@ -1,0 +1,180 @@
+/*
+ * lvb200.h - C ABI of the B200-native Long-VITA hot path (long-context forward / backward).
+ *
+ * This is the drop-in boundary.  The reference has no native layer: on
+ * GPU it reaches flash-attn 2, TransformerEngine, apex and cuBLAS through Python.  Every entry
+ * point below replaces one of those third-party calls; the comment on each cites the reference
+ * call site (path:line relative to the Long-VITA repository) whose arithmetic it reproduces.
+ *
+ * Conventions
+ *   - plain device pointers and sizes only; no framework types cross this boundary;
+ *   - the caller owns every buffer (inputs, outputs, workspace); nothing is allocated here
+ *     except per-process tensor-map caches;
+ *   - every call takes the CUDA stream to launch on and is asynchronous with respect to the host;
+ *   - return value: 0 on success, a negative LV_E* code otherwise; lv_last_error() returns a
+ *     thread-local description of the last failure on the calling thread;
+ *   - activations are bfloat16 unless stated otherwise ("bf16" below), statistics are float;
+ *   - all functions are re-entrant and keep no mutable global state other than the
+ *     once-per-process symmetric KV heap registered through lv_cp_register().
+ */
+#ifndef LVB200_H_
+#define LVB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* lv_stream_t; /* cudaStream_t */
+
+#define LV_OK 0
+#define LV_EINVAL (-1)    /* bad argument (shape, stride, alignment)            */
+#define LV_ECUDA (-2)     /* a CUDA runtime / driver call failed                */
+#define LV_ENOTSUP (-3)   /* valid request this build does not implement        */
+#define LV_ESTATE (-4)    /* context-parallel heap not registered / bad epoch   */
+
+/* ABI version: major * 1000 + minor. */
+int lv_version(void);
+/* Thread-local text of the last error returned on this thread ("" if none). */
+const char* lv_last_error(void);
+/* Number of kernels this library has launched in this process (all threads). */
+int64_t lv_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention (forward).
+ *
+ * Replaces flash_attn_func / _flash_attention_forward as called from
+ *   long_vita_megatron/core/transformer/dot_product_attention.py:318-326 (ViT, non-causal) and
+ *   :374-390 (LLM, causal, GQA kv heads not pre-expanded, :176-184), and from
+ *   long_vita/models/long_vita_qwen2_intern/flash_attention.py:52-74 (HF ViT).
+ *
+ * out[b, i, h, :] = sum_j softmax_j(scale * q[b,i,h,:] . k[b,j,h/(hq/hkv),:]) v[b,j,h/(hq/hkv),:]
+ * lse[b, h, i]    = log sum_j exp(scale * q.k)          (natural log; float; may be NULL)
+ *
+ * Strides are in elements; the head dimension is contiguous (stride 1).  Supported head_dim: 64,
+ * 128.  q_pos0 / causal: query row i has global position q_seg_pos[i / q_seg_len] + i % q_seg_len
+ * and key row j has position kv_pos0 + j; with causal != 0 a key is visible iff
+ * key_pos <= query_pos.  For a plain causal call use q_seg_len = sq, q_seg_pos = {sk - sq, 0},
+ * kv_pos0 = 0 (bottom-right aligned, the flash-attn >= 2.1 convention the reference relies on).
+ * The zig-zag context-parallel layout (training/utils.py:329-341) is q_seg_len = sq / 2,
+ * q_seg_pos = {r * c, (2 cp - 1 - r) * c}.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lv_attn_params {
+  const void* q;  /* bf16 [b, sq, hq, d]  (any strides, d contiguous) */
+  const void* k;  /* bf16 [b, sk, hkv, d] */
+  const void* v;  /* bf16 [b, sk, hkv, d] */
+  void* out;      /* bf16 [b, sq, hq, d]  */
+  float* lse;     /* float [b, hq, sq] contiguous, or NULL */
+  int64_t batch, sq, sk, hq, hkv, d;
+  int64_t q_strides[3];   /* batch, seq, head */
+  int64_t k_strides[3];
+  int64_t v_strides[3];
+  int64_t o_strides[3];
+  float scale;            /* softmax scale, e.g. 1/sqrt(d) */
+  int32_t causal;         /* 0 / 1 */
+  int64_t q_seg_len;      /* rows per query segment (sq if one segment); multiple of 256 if < sq */
+  int64_t q_seg_pos[2];   /* global position of the first row of each query segment */
+  int64_t kv_pos0;        /* global position of key row 0 */
+} lv_attn_params;
+
+int lv_attn_fwd(const lv_attn_params* p, lv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Token-wise memory-bound operators (HBM roofline).
+ * ------------------------------------------------------------------------------------------ */
+
+/* RMSNorm: y = bf16( bf16(x_f32 * rsqrt(mean(x^2) + eps)) * w ).
+ * long_vita_megatron/core/transformer/custom_layers/transformer_engine.py:74-79 (and the HF
+ * Qwen2RMSNorm the reference instantiates, modeling_long_vita.py:57).  If `residual` is not NULL
+ * the kernel first forms h = x + residual (bf16 rounding), writes h to `sum_out`, and normalises
+ * h (the bias-dropout-add of transformer_layer.py:211-213 fused with the following norm). */
+int lv_rmsnorm(const void* x, const void* residual, const void* w, void* y, void* sum_out, int64_t rows,
+               int64_t cols, float eps, lv_stream_t stream);
+
+/* LayerNorm with affine weight/bias (ViT norm1/norm2, eps 1e-6: modeling_intern_vit.py:205-206;
+ * pre-projection LayerNorm over 4096: resampler_projector.py:17,30). fp32 statistics. */
+int lv_layernorm(const void* x, const void* w, const void* b, void* y, int64_t rows, int64_t cols, float eps,
+                 lv_stream_t stream);
+
+/* Rotary table: cos/sin (bf16, [n, dim]) of pos[i] * inv_freq[j % (dim/2)], the
+ * cat(freqs, freqs) layout of rotary_pos_embedding.py:102-106; pos is int64 (position_ids gather
+ * of :114-117 and the zig-zag slice of :36-47 are both expressed by passing the right pos). */
+int lv_rope_table(const int64_t* pos, const float* inv_freq, void* cos_out, void* sin_out, int64_t n,
+                  int64_t dim, lv_stream_t stream);
+
+/* Rotary embedding, non-interleaved (rotate_half): t = t*cos + rotate_half(t)*sin with the bf16
+ * rounding sequence of apply_rotary_pos_emb_bshd, rotary_pos_embedding.py:181-204 (== HF
+ * apply_rotary_pos_emb).  x is [n_tok, heads, dim] with element strides (tok, head), dim
+ * contiguous; out may alias x. */
+int lv_rope(const void* x, void* out, const void* cos_t, const void* sin_t, int64_t n_tok, int64_t heads,
+            int64_t dim, int64_t x_tok_stride, int64_t x_head_stride, int64_t o_tok_stride,
+            int64_t o_head_stride, lv_stream_t stream);
+
+/* SwiGLU: out[r, i] = silu(gu[r, i]) * gu[r, inter + i]; fc1 = cat(gate, up)
+ * (tools/hf2mcore_long_vita.py:502-504), HF Qwen2MLP act_fn(gate_proj(x)) * up_proj(x). */
+int lv_swiglu(const void* gate_up, void* out, int64_t rows, int64_t inter, lv_stream_t stream);
+
+/* y = gelu(x + bias); approx = 0: exact erf GELU (InternViT, pretrain_long_vita.py:206,
+ * resampler_projector.py:21); approx = 1: tanh GELU (SigLIP, pretrain_long_vita.py:291).
+ * bias may be NULL. */
+int lv_bias_gelu(const void* x, const void* bias, void* y, int64_t rows, int64_t cols, int32_t approx,
+                 lv_stream_t stream);
+
+/* Layer-scale residual: out = x + (y + bias) * ls   (intern_vit_model.py:63,77;
+ * modeling_intern_vit.py:224-226).  bias may be NULL; ls may be NULL (plain residual add). */
+int lv_ls_residual(const void* x, const void* y, const void* bias, const void* ls, void* out, int64_t rows,
+                   int64_t cols, lv_stream_t stream);
+
+/* Pixel-shuffle x0.5 of ViT tokens without the class token:
+ * in [n, 1 + hw*hw, c] (cls at index 0, dropped: modeling_long_vita.py:97) ->
+ * out [n, (hw/2)^2, 4c]; pure permutation, bit-exact with resampler_projector.py:36-46 /
+ * pretrain_long_vita.py:572-582.  has_cls selects whether row 0 is skipped. */
+int lv_pixel_shuffle(const void* x, void* out, int64_t n, int64_t hw, int64_t c, int32_t has_cls,
+                     lv_stream_t stream);
+
+/* Embedding gather + image-feature scatter:
+ * out[t, :] = table[ids[t], :]; then out[dst_idx[i], :] = feat[src_idx[i], :] (src_idx NULL =>
+ * identity).  language_model_embedding.py:102-131, modeling_long_vita.py:138-147.  Index
+ * arithmetic is int64 and bit-exact.  Duplicate dst_idx are applied in increasing i order only
+ * if `n_scatter` is small; callers pass unique targets (the reference has unique targets). */
+int lv_embed_scatter(const int64_t* ids, const void* table, int64_t vocab, const void* feat,
+                     const int64_t* src_idx, const int64_t* dst_idx, int64_t n_scatter, void* out,
+                     int64_t n_tok, int64_t hidden, lv_stream_t stream);
+
+/* Row gather / scatter used by the logit-masked LM head:
+ * gather:  out[i, :] = x[idx[i], :]                     (masked_select, layers.py:402-407)
+ * scatter: out[idx[i], :] = x[i, :], other rows zero    (masked_scatter, layers.py:446-451) */
+int lv_row_gather(const void* x, const int64_t* idx, void* out, int64_t n_idx, int64_t cols,
+                  lv_stream_t stream);
+int lv_row_scatter_zero(const void* x, const int64_t* idx, void* out, int64_t n_idx, int64_t n_rows_out,
+                        int64_t cols, lv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense linears (tensor-core roofline).  C[M,N] = act(A[M,K] . W[N,K]^T + bias[N]), bf16 in,
+ * fp32 accumulate, bf16 out.  Replaces torch.matmul / te.Linear at layers.py:270,409, the ViT
+ * qkv/proj/fc1/fc2 (modeling_intern_vit.py:131,141,190-191) and the projector
+ * (resampler_projector.py:19-23).  K must be a multiple of 8 (16-byte rows).
+ * act: 0 none, 1 exact GELU, 2 tanh GELU, 3 SwiGLU over interleaved column pairs is NOT used;
+ * SwiGLU is a separate pass (lv_swiglu).  lda / ldw / ldc are row strides in elements.
+ * ------------------------------------------------------------------------------------------ */
+int lv_gemm_bias_act(const void* A, const void* W, const void* bias, void* C, int64_t M, int64_t N,
+                     int64_t K, int64_t lda, int64_t ldw, int64_t ldc, int32_t act, lv_stream_t stream);
+
+/* Patch embedding of 14x14 non-overlapping patches (Conv2d(3, C, k=14, s=14),
+ * modeling_intern_vit.py:79-81,98; intern_vit_model.py:139-145,203) + class token + learned
+ * position embedding (modeling_intern_vit.py:100-107):
+ * out[n, 0, :] = cls + pos[0]; out[n, 1 + p, :] = bf16(W . patch(n, p) + bias) + pos[1 + p].
+ * images bf16 [n, 3, img, img]; W bf16 [C, Kpad] = the conv weight flattened to [C, 3*ps*ps] and
+ * zero-padded per row to Kpad = 3*ps*ps rounded up to a multiple of 64 (done once at load time);
+ * out bf16 [n, 1 + (img/ps)^2, C].  `ws` is caller workspace of lv_patch_embed_ws_bytes() bytes
+ * (the im2col matrix and the un-offset GEMM result). */
+int64_t lv_patch_embed_ws_bytes(int64_t n, int64_t img, int64_t ps, int64_t C);
+int lv_patch_embed(const void* images, const void* W, const void* bias, const void* cls, const void* pos,
+                   void* out, void* ws, int64_t n, int64_t img, int64_t ps, int64_t C,
+                   lv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVB200_H_ */

@@ -1,0 +1,523 @@
+// Fused attention forward for sm_100a: softmax(scale * Q K^T + mask) V with online softmax, GQA,
+// causal / zig-zag-causal / no mask, LSE output.
+//
+// One persistent CTA per SM, 12 warps, warp-specialised:
+//   warp 0      TMA producer: Q tiles (2 x 128 rows per work item) and a K ring + V ring of
+//               128-row tiles, 128-byte swizzle, mbarrier completion
+//   warp 1      tcgen05.mma issuer (one elected thread).  S_t = Q_t K^T (SS form, both operands
+//               from shared memory) into TMEM; O_t += P_t V (TS form: P read from TMEM, V from
+//               shared memory as an MN-major operand).  Two query tiles are ping-ponged so the
+//               tensor pipe works on tile 1-t while the softmax warps work on tile t:
+//               QK0(j) PV1(j-1) QK1(j) PV0(j) ...
+//   warps 2-3   idle in this kernel (the context-parallel variant uses them to pull remote K/V)
+//   warps 4-7   softmax warpgroup for query tile 0 (one thread per query row)
+//   warps 8-11  softmax warpgroup for query tile 1
+// A softmax thread reads its row of S from TMEM (tcgen05.ld), keeps a running max in the log2
+// domain, rescales O only when the max grew by more than 2^8 (lazy rescale: P <= 256 stays well
+// inside bf16/fp32 range), writes P (bf16) back over S in TMEM (tcgen05.st) and at the end
+// normalises O, stages it in the (now free) Q shared-memory tile and stores it with TMA.
+//
+// TMEM map (512 columns): S0/P0 @0, S1/P1 @128, O0 @256, O1 @256 + D.
+//
+// Reference call sites replaced: flash_attn_func / _flash_attention_forward in
+// long_vita_megatron/core/transformer/dot_product_attention.py:318-326, 374-390 and
+// long_vita/models/long_vita_qwen2_intern/flash_attention.py:52-74.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace lv {
+
+constexpr int A_BM = 128;   // query rows per tile
+constexpr int A_BN = 128;   // key rows per tile
+constexpr int A_THREADS = 384;
+
+struct AttnKParams {
+  int batch, sq, sk, hq, hkv;
+  int causal;
+  float scale_log2;
+  int q_seg_len;
+  long long q_seg_pos0, q_seg_pos1, kv_pos0;
+  int n_qblk;      // ceil(sq / 256)
+  int n_items;     // batch * hq * n_qblk
+  float* lse;
+};
+
+template <int D>
+struct AttnCfg {
+  static constexpr int KV_STAGES = (D == 128) ? 2 : 4;
+  static constexpr int TILE_BYTES = 128 * D * 2;           // one 128-row tile of Q / K / V
+  static constexpr int BOXES = D / 64;                     // 64-column (128-byte) TMA boxes per row
+  static constexpr int SMEM_Q = 2 * TILE_BYTES;
+  static constexpr int SMEM_K = KV_STAGES * TILE_BYTES;
+  static constexpr int SMEM_V = KV_STAGES * TILE_BYTES;
+  static constexpr int SMEM_BAR = 512;
+  static constexpr int SMEM_TOTAL = SMEM_Q + SMEM_K + SMEM_V + SMEM_BAR + 1024;
+  static constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 256 + D;
+};
+
+struct WorkItem {
+  int b, h, kvh, qblk;
+  int n[2];          // kv tiles each query tile attends to (0: nothing to do)
+  long long qpos[2]; // global position of row 0 of each query tile
+  int row0[2];       // local row index of row 0 of each query tile
+};
+
+__device__ __forceinline__ WorkItem decode_item(const AttnKParams& p, int item) {
+  WorkItem w;
+  const int G = p.hq / p.hkv;
+  const int g = item % G;
+  int r = item / G;
+  const int rank = r % p.n_qblk;
+  r /= p.n_qblk;
+  w.kvh = r % p.hkv;
+  w.b = r / p.hkv;
+  w.h = w.kvh * G + g;
+  w.qblk = p.causal ? (p.n_qblk - 1 - rank) : rank;   // heaviest causal blocks first
+  const int n_kv_tiles = (p.sk + A_BN - 1) / A_BN;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int row0 = w.qblk * 256 + t * A_BM;
+    w.row0[t] = row0;
+    const int seg = row0 / p.q_seg_len;
+    w.qpos[t] = (seg == 0 ? p.q_seg_pos0 : p.q_seg_pos1) + (row0 - seg * p.q_seg_len);
+    int n = 0;
+    if (row0 < p.sq) {
+      n = n_kv_tiles;
+      if (p.causal) {
+        const long long hi = w.qpos[t] + (A_BM - 1) - p.kv_pos0;  // last visible key index for the tile
+        if (hi < 0)
+          n = 0;
+        else {
+          const long long lim = hi / A_BN + 1;
+          if (lim < n) n = (int)lim;
+        }
+      }
+    }
+    w.n[t] = n;
+  }
+  return w;
+}
+
+template <int D>
+__global__ void __launch_bounds__(A_THREADS, 1)
+    attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                    const AttnKParams p) {
+  using Cfg = AttnCfg<D>;
+  constexpr int NS = Cfg::KV_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::SMEM_Q;
+  uint8_t* sV = sK + Cfg::SMEM_K;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Cfg::SMEM_V);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* q_empty = bars + 2;       // [2]
+  uint64_t* k_full = bars + 4;        // [NS]
+  uint64_t* k_empty = bars + 4 + NS;  // [NS]
+  uint64_t* v_full = bars + 4 + 2 * NS;
+  uint64_t* v_empty = bars + 4 + 3 * NS;
+  uint64_t* s_full = bars + 4 + 4 * NS;   // [2]
+  uint64_t* p_full = s_full + 2;          // [2]
+  uint64_t* o_full = p_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+    }
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    if (lane == 0) {
+      uint32_t item_cnt = 0, kcnt = 0, vcnt = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+        const WorkItem w = decode_item(p, item);
+        const int nmax = max(w.n[0], w.n[1]);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&q_empty[t], (item_cnt & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[t], Cfg::TILE_BYTES);
+          for (int bx = 0; bx < Cfg::BOXES; ++bx)
+            tma_load_4d(sQ + t * Cfg::TILE_BYTES + bx * 16384, &tmQ, &q_full[t], bx * 64, w.row0[t], w.h, w.b,
+                        kEvictFirst);
+        }
+        for (int j = 0; j < nmax; ++j) {
+          {
+            const int st = kcnt % NS;
+            mbar_wait(&k_empty[st], ((kcnt / NS) & 1) ^ 1);
+            mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
+            for (int bx = 0; bx < Cfg::BOXES; ++bx)
+              tma_load_4d(sK + st * Cfg::TILE_BYTES + bx * 16384, &tmK, &k_full[st], bx * 64, j * A_BN, w.kvh, w.b,
+                          kEvictLast);
+            ++kcnt;
+          }
+          {
+            const int st = vcnt % NS;
+            mbar_wait(&v_empty[st], ((vcnt / NS) & 1) ^ 1);
+            mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
+            for (int bx = 0; bx < Cfg::BOXES; ++bx)
+              tma_load_4d(sV + st * Cfg::TILE_BYTES + bx * 16384, &tmV, &v_full[st], bx * 64, j * A_BN, w.kvh, w.b,
+                          kEvictLast);
+            ++vcnt;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(A_BM, A_BN, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(A_BM, D, 0, 1);
+      const uint32_t tS[2] = {tmem_base + Cfg::TM_S0, tmem_base + Cfg::TM_S1};
+      const uint32_t tO[2] = {tmem_base + Cfg::TM_O0, tmem_base + Cfg::TM_O1};
+      uint32_t item_cnt = 0, kcnt = 0, vcnt_wait = 0, vcnt_rel = 0;
+      uint32_t pcnt[2] = {0, 0};
+
+      auto issue_qk = [&](int t, int kst) {
+        const uint32_t qa = smem_u32(sQ + t * Cfg::TILE_BYTES);
+        const uint32_t ka = smem_u32(sK + kst * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
+          umma_ss(tS[t], make_smem_desc(qa + off, 16, 1024), make_smem_desc(ka + off, 16, 1024), idesc_qk,
+                  kk != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int vst, bool accumulate) {
+        const uint32_t va = smem_u32(sV + vst * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < A_BN / 16; ++kk) {
+          // A: P_t rows in TMEM, 16 bf16 (= 8 columns) per k-step.  B: V tile, MN-major: 16 key rows
+          // (2 KB) per k-step, the second 64 head-dim columns live one 16 KB box further.
+          umma_ts(tO[t], tS[t] + kk * 8, make_smem_desc(va + kk * 2048, 16384, 1024), idesc_pv,
+                  (accumulate || kk != 0) ? 1u : 0u);
+        }
+      };
+
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+        const WorkItem w = decode_item(p, item);
+        const int n0 = w.n[0], n1 = w.n[1];
+        const int nmax = max(n0, n1);
+        mbar_wait(&q_full[0], item_cnt & 1);
+        mbar_wait(&q_full[1], item_cnt & 1);
+        tc_fence_after();
+        const uint32_t vbase = vcnt_wait;   // V tile j of this item has ring counter vbase + j
+        for (int j = 0; j <= nmax; ++j) {
+          int kst = 0;
+          if (j < nmax) {
+            kst = kcnt % NS;
+            mbar_wait(&k_full[kst], (kcnt / NS) & 1);
+            tc_fence_after();
+          }
+          if (j < n0) {
+            issue_qk(0, kst);
+            umma_commit(&s_full[0]);
+          }
+          if (j >= 1) {
+            if (j - 1 < n1) {
+              const uint32_t vc = vbase + (j - 1);
+              if (vc == vcnt_wait) {
+                mbar_wait(&v_full[vc % NS], (vc / NS) & 1);
+                ++vcnt_wait;
+              }
+              mbar_wait(&p_full[1], pcnt[1] & 1);
+              ++pcnt[1];
+              tc_fence_after();
+              issue_pv(1, vc % NS, j - 1 > 0);
+              if (j - 1 == n1 - 1) umma_commit(&o_full[1]);
+            }
+            // V(j-1) has now been consumed by every PV that needs it
+            umma_commit(&v_empty[vcnt_rel % NS]);
+            ++vcnt_rel;
+          }
+          if (j < n1) {
+            issue_qk(1, kst);
+            umma_commit(&s_full[1]);
+          }
+          if (j < nmax) {
+            umma_commit(&k_empty[kst]);
+            ++kcnt;
+          }
+          if (j < n0) {
+            const uint32_t vc = vbase + j;
+            if (vc == vcnt_wait) {
+              mbar_wait(&v_full[vc % NS], (vc / NS) & 1);
+              ++vcnt_wait;
+            }
+            mbar_wait(&p_full[0], pcnt[0] & 1);
+            ++pcnt[0];
+            tc_fence_after();
+            issue_pv(0, vc % NS, j > 0);
+            if (j == n0 - 1) umma_commit(&o_full[0]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================== softmax / epilogue warpgroups ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int t = (warp - 4) >> 2;                // query tile handled by this warpgroup
+    const int quad = warp & 3;                    // TMEM lane quadrant of this warp
+    const int row = quad * 32 + lane;             // row inside the 128-row tile
+    const int wg_tid = (warp - 4 - 4 * t) * 32 + lane;
+    const uint32_t lane_base = uint32_t(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + (t == 0 ? Cfg::TM_S0 : Cfg::TM_S1);
+    const uint32_t tO = tmem_base + lane_base + (t == 0 ? Cfg::TM_O0 : Cfg::TM_O1);
+    uint8_t* stage = sQ + t * Cfg::TILE_BYTES;
+    uint32_t item_cnt = 0, scnt = 0, ocnt = 0;
+
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+      const WorkItem w = decode_item(p, item);
+      const int n = w.n[t];
+      const long long qpos = w.qpos[t] + row;           // global position of this thread's query row
+      float m_used = 0.f, l = 0.f;
+      for (int j = 0; j < n; ++j) {
+        mbar_wait(&s_full[t], scnt & 1);
+        ++scnt;
+        tc_fence_after();
+        uint32_t s[4][32];
+        tmem_ld32(tS + 0, s[0]);
+        tmem_ld32(tS + 32, s[1]);
+        tmem_ld32(tS + 64, s[2]);
+        tmem_ld32(tS + 96, s[3]);
+        tmem_wait_ld();
+
+        // ---- mask (only diagonal tiles and the ragged last key tile) ----
+        const long long kidx0 = (long long)j * A_BN;
+        const bool ragged = kidx0 + A_BN > p.sk;
+        const bool diag = p.causal && (p.kv_pos0 + kidx0 + A_BN - 1 > w.qpos[t]);
+        if (ragged || diag) {
+          long long lim = p.sk - kidx0;                               // first invalid column (ragged)
+          if (p.causal) {
+            const long long c = qpos - p.kv_pos0 - kidx0 + 1;         // first masked column (causal)
+            if (c < lim) lim = c;
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= lim) s[c][i] = 0xff800000u;  // -inf
+        }
+
+        // ---- row max ----
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          mx0 = fmax3(mx0, __uint_as_float(s[0][i]), __uint_as_float(s[0][i + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(s[1][i]), __uint_as_float(s[1][i + 1]));
+          mx2 = fmax3(mx2, __uint_as_float(s[2][i]), __uint_as_float(s[2][i + 1]));
+          mx3 = fmax3(mx3, __uint_as_float(s[3][i]), __uint_as_float(s[3][i + 1]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+
+        // ---- lazy rescale ----
+        if (j == 0) {
+          m_used = (mx == -INFINITY) ? 0.f : mx;
+        } else {
+          const bool grow = mx > m_used + 8.f;
+          if (__any_sync(0xffffffffu, grow)) {
+            const float m_new = fmaxf(m_used, mx);
+            const float alpha = ex2(m_used - m_new);
+            m_used = m_new;
+            l *= alpha;
+#pragma unroll 1
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(tO + c * 32, o);
+            }
+          }
+        }
+
+        // ---- P = exp2(S * scale_log2 - m), row sum, bf16 pack, store over S in TMEM ----
+        const float neg_m = -m_used;
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float p0 = ex2(fmaf(__uint_as_float(s[c][i + 0]), p.scale_log2, neg_m));
+            const float p1 = ex2(fmaf(__uint_as_float(s[c][i + 1]), p.scale_log2, neg_m));
+            const float p2 = ex2(fmaf(__uint_as_float(s[c][i + 2]), p.scale_log2, neg_m));
+            const float p3 = ex2(fmaf(__uint_as_float(s[c][i + 3]), p.scale_log2, neg_m));
+            l0 += p0;
+            l1 += p1;
+            l2 += p2;
+            l3 += p3;
+            pk[i / 2] = pack_bf16(p0, p1);
+            pk[i / 2 + 1] = pack_bf16(p2, p3);
+          }
+          tmem_st16(tS + c * 16, pk);
+        }
+        l += (l0 + l1) + (l2 + l3);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+
+      // ---------------- epilogue: O / l -> bf16 -> smem (swizzled) -> TMA store; LSE ----------------
+      const float inv_l = (n > 0 && l > 0.f) ? 1.f / l : 0.f;
+      if (n > 0) {
+        mbar_wait(&o_full[t], ocnt & 1);
+        ++ocnt;
+        tc_fence_after();
+      } else {
+        mbar_wait(&q_full[t], item_cnt & 1);   // the Q load into the staging tile must have landed
+      }
+#pragma unroll 1
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[32];
+        if (n > 0) {
+          tmem_ld32(tO + c * 32, o);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0u;
+        }
+        uint8_t* box = stage + (c >> 1) * 16384 + row * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[8 * q + 0]) * inv_l, __uint_as_float(o[8 * q + 1]) * inv_l);
+          v.y = pack_bf16(__uint_as_float(o[8 * q + 2]) * inv_l, __uint_as_float(o[8 * q + 3]) * inv_l);
+          v.z = pack_bf16(__uint_as_float(o[8 * q + 4]) * inv_l, __uint_as_float(o[8 * q + 5]) * inv_l);
+          v.w = pack_bf16(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l);
+          const int chunk = (c & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(box + ((chunk ^ (row & 7)) << 4)) = v;
+        }
+      }
+      tc_fence_before();
+      if (p.lse != nullptr && w.row0[t] + row < p.sq) {
+        const float lse = (n > 0 && l > 0.f) ? (m_used + log2f(l)) * 0.69314718055994530942f : -INFINITY;
+        p.lse[((long long)w.b * p.hq + w.h) * p.sq + w.row0[t] + row] = lse;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + t, 128);
+      if (wg_tid == 0) {
+        if (w.row0[t] < p.sq) {
+          for (int bx = 0; bx < Cfg::BOXES; ++bx) tma_store_4d(&tmO, stage + bx * 16384, bx * 64, w.row0[t], w.h, w.b);
+          tma_store_commit();
+          tma_store_wait_read0();
+        }
+        mbar_arrive(&q_empty[t]);   // Q_t / staging tile may be overwritten by the next item's Q load
+      }
+    }
+    if (wg_tid == 0) tma_store_wait_all0();
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <int D>
+static int launch_attn(const lv_attn_params* a, cudaStream_t s) {
+  using Cfg = AttnCfg<D>;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  const uint32_t box[4] = {64, 128, 1, 1};
+  {
+    const uint64_t dims[4] = {(uint64_t)D, (uint64_t)a->sq, (uint64_t)a->hq, (uint64_t)a->batch};
+    const uint64_t str[4] = {2, (uint64_t)a->q_strides[1] * 2, (uint64_t)a->q_strides[2] * 2, (uint64_t)a->q_strides[0] * 2};
+    int r = encode_tmap_bf16(&tmQ, a->q, 4, dims, str, box, true);
+    if (r) return r;
+    const uint64_t ostr[4] = {2, (uint64_t)a->o_strides[1] * 2, (uint64_t)a->o_strides[2] * 2, (uint64_t)a->o_strides[0] * 2};
+    r = encode_tmap_bf16(&tmO, a->out, 4, dims, ostr, box, true);
+    if (r) return r;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)D, (uint64_t)a->sk, (uint64_t)a->hkv, (uint64_t)a->batch};
+    const uint64_t kstr[4] = {2, (uint64_t)a->k_strides[1] * 2, (uint64_t)a->k_strides[2] * 2, (uint64_t)a->k_strides[0] * 2};
+    const uint64_t vstr[4] = {2, (uint64_t)a->v_strides[1] * 2, (uint64_t)a->v_strides[2] * 2, (uint64_t)a->v_strides[0] * 2};
+    int r = encode_tmap_bf16(&tmK, a->k, 4, dims, kstr, box, true);
+    if (r) return r;
+    r = encode_tmap_bf16(&tmV, a->v, 4, dims, vstr, box, true);
+    if (r) return r;
+  }
+  AttnKParams p;
+  p.batch = (int)a->batch;
+  p.sq = (int)a->sq;
+  p.sk = (int)a->sk;
+  p.hq = (int)a->hq;
+  p.hkv = (int)a->hkv;
+  p.causal = a->causal ? 1 : 0;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.q_seg_len = (int)a->q_seg_len;
+  p.q_seg_pos0 = a->q_seg_pos[0];
+  p.q_seg_pos1 = a->q_seg_pos[1];
+  p.kv_pos0 = a->kv_pos0;
+  p.n_qblk = (int)((a->sq + 255) / 256);
+  p.n_items = (int)(a->batch * a->hq * p.n_qblk);
+  p.lse = a->lse;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
+    attr_set = true;
+  }
+  const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
+  attn_fwd_kernel<D><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p);
+  LV_CHECK_LAUNCH("attn_fwd_kernel");
+  return LV_OK;
+}
+
+}  // namespace lv
+
+using namespace lv;
+
+extern "C" int lv_attn_fwd(const lv_attn_params* a, lv_stream_t stream) {
+  LV_CHECK_ARG(a != nullptr, "lv_attn_fwd: null params");
+  LV_CHECK_ARG(a->q && a->k && a->v && a->out, "lv_attn_fwd: null tensor pointer");
+  LV_CHECK_ARG(a->d == 64 || a->d == 128, "lv_attn_fwd: head_dim %lld not supported (64, 128)", (long long)a->d);
+  LV_CHECK_ARG(a->batch > 0 && a->sq > 0 && a->sk > 0 && a->hq > 0 && a->hkv > 0, "lv_attn_fwd: empty shape");
+  LV_CHECK_ARG(a->hq % a->hkv == 0, "lv_attn_fwd: hq=%lld is not a multiple of hkv=%lld", (long long)a->hq, (long long)a->hkv);
+  LV_CHECK_ARG(a->sq < (1ll << 30) && a->sk < (1ll << 30), "lv_attn_fwd: sequence too long");
+  LV_CHECK_ARG(a->batch * a->hq * ((a->sq + 255) / 256) < (1ll << 31), "lv_attn_fwd: too many work items");
+  LV_CHECK_ARG(a->q_seg_len > 0 && a->q_seg_len <= a->sq, "lv_attn_fwd: q_seg_len=%lld out of range", (long long)a->q_seg_len);
+  if (a->q_seg_len < a->sq) {
+    LV_CHECK_ARG(a->q_seg_len % 256 == 0 && a->sq <= 2 * a->q_seg_len, "lv_attn_fwd: segmented queries need q_seg_len %% 256 == 0 and at most two segments");
+  }
+  for (int i = 0; i < 3; ++i)
+    LV_CHECK_ARG(a->q_strides[i] % 8 == 0 && a->k_strides[i] % 8 == 0 && a->v_strides[i] % 8 == 0 && a->o_strides[i] % 8 == 0,
+                 "lv_attn_fwd: strides must be multiples of 8 elements (16 bytes)");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (a->d == 128) return launch_attn<128>(a, s);
+  return launch_attn<64>(a, s);
+}

@@ -1,0 +1,52 @@
+// Host-side plumbing shared by every translation unit of liblvb200.so: error reporting for the
+// C ABI, launch accounting, and TMA tensor-map encoding through the driver entry point (so the
+// library does not link libcuda directly).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/lvb200.h"
+
+namespace lv {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int sm_count();
+
+// Encode a bf16 tiled tensor map.  dims/strides innermost-first; strides in BYTES for dims 1..rank-1
+// (dim 0 is contiguous).  box = tile extents, innermost-first.  swizzle128: 128-byte swizzle
+// (box[0] * 2 bytes must be <= 128), otherwise no swizzle.
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
+#define LV_CHECK_ARG(cond, ...)   \
+  do {                            \
+    if (!(cond)) {                \
+      lv::set_error(__VA_ARGS__); \
+      return LV_EINVAL;           \
+    }                             \
+  } while (0)
+
+#define LV_CHECK_CUDA(expr)                                                                     \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      lv::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return LV_ECUDA;                                                                          \
+    }                                                                                           \
+  } while (0)
+
+#define LV_CHECK_LAUNCH(name)                                                             \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      lv::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));             \
+      return LV_ECUDA;                                                                    \
+    }                                                                                     \
+    lv::count_launch();                                                                   \
+  } while (0)
+
+}  // namespace lv

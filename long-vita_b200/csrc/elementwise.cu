@@ -1,0 +1,541 @@
+// Token-wise HBM-bound operators of the Long-VITA hot path: RMSNorm(+residual), LayerNorm, RoPE
+// table + apply, SwiGLU, bias+GELU, layer-scale residual, pixel-shuffle, embedding gather +
+// feature scatter, row gather / scatter.  One pass over the data, 16-byte accesses, fp32 math,
+// and the bf16 rounding points of the reference's eager PyTorch sequence (cited per kernel) so
+// results match the oracle bit-for-bit wherever the arithmetic is exactly representable.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace lv {
+
+struct alignas(16) Vec8 {
+  __nv_bfloat162 h[4];
+};
+
+__device__ __forceinline__ Vec8 ldg_vec(const void* p) {
+  return *reinterpret_cast<const Vec8*>(p);
+}
+__device__ __forceinline__ Vec8 ldg_stream(const void* p) {
+  Vec8 v;
+  uint32_t* u = reinterpret_cast<uint32_t*>(&v);
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_vec(void* p, const Vec8& v) { *reinterpret_cast<Vec8*>(p) = v; }
+
+__device__ __forceinline__ void unpack(const Vec8& v, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(v.h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ Vec8 pack(const float (&f)[8]) {
+  Vec8 v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v.h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+template <int TPR>
+__device__ __forceinline__ float row_reduce_sum(float v, float* smem, int row_in_cta, int tid_in_row) {
+  // TPR threads cooperate on one row; TPR is a power of two, <= 32 or a multiple of 32.
+  if (TPR <= 32) {
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  } else {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    constexpr int W = TPR / 32;
+    int w = tid_in_row >> 5;
+    __syncthreads();  // protect smem reuse across successive reductions
+    if ((tid_in_row & 31) == 0) smem[row_in_cta * W + w] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < W; ++i) t += smem[row_in_cta * W + i];
+    return t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RMSNorm (+ fused residual add)
+// ---------------------------------------------------------------------------------------------
+template <int TPR, int VPT>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const __nv_bfloat16* __restrict__ x,
+                                                      const __nv_bfloat16* __restrict__ res,
+                                                      const __nv_bfloat16* __restrict__ w,
+                                                      __nv_bfloat16* __restrict__ y,
+                                                      __nv_bfloat16* __restrict__ sum_out, int64_t rows, int cols,
+                                                      float eps) {
+  constexpr int RPC = 256 / TPR;
+  __shared__ float red[RPC * (TPR > 32 ? TPR / 32 : 1)];
+  const int row_in_cta = threadIdx.x / TPR;
+  const int t = threadIdx.x % TPR;
+  const int64_t row = (int64_t)blockIdx.x * RPC + row_in_cta;
+  const bool row_ok = row < rows;
+  const int nvec = cols / 8;
+  float v[VPT][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = t + i * TPR;
+    if (row_ok && c < nvec) {
+      unpack(ldg_stream(x + row * cols + c * 8), v[i]);
+      if (res != nullptr) {
+        float r[8];
+        unpack(ldg_stream(res + row * cols + c * 8), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = bf16r(v[i][j] + r[j]);
+        if (sum_out != nullptr) stg_vec(sum_out + row * cols + c * 8, pack(v[i]));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+  }
+  ss = row_reduce_sum<TPR>(ss, red, row_in_cta, t);
+  const float rstd = rsqrtf(ss / (float)cols + eps);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = t + i * TPR;
+    if (row_ok && c < nvec) {
+      float wv[8], o[8];
+      unpack(ldg_vec(w + c * 8), wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = bf16r(v[i][j] * rstd) * wv[j];
+      stg_vec(y + row * cols + c * 8, pack(o));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm
+// ---------------------------------------------------------------------------------------------
+template <int TPR, int VPT>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x,
+                                                        const __nv_bfloat16* __restrict__ w,
+                                                        const __nv_bfloat16* __restrict__ b,
+                                                        __nv_bfloat16* __restrict__ y, int64_t rows, int cols,
+                                                        float eps) {
+  constexpr int RPC = 256 / TPR;
+  __shared__ float red[RPC * (TPR > 32 ? TPR / 32 : 1)];
+  const int row_in_cta = threadIdx.x / TPR;
+  const int t = threadIdx.x % TPR;
+  const int64_t row = (int64_t)blockIdx.x * RPC + row_in_cta;
+  const bool row_ok = row < rows;
+  const int nvec = cols / 8;
+  float v[VPT][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = t + i * TPR;
+    if (row_ok && c < nvec) {
+      unpack(ldg_stream(x + row * cols + c * 8), v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+  }
+  s = row_reduce_sum<TPR>(s, red, row_in_cta, t);
+  const float mean = s / (float)cols;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = t + i * TPR;
+    if (row_ok && c < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d = v[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  q = row_reduce_sum<TPR>(q, red, row_in_cta, t);
+  const float rstd = rsqrtf(q / (float)cols + eps);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = t + i * TPR;
+    if (row_ok && c < nvec) {
+      float wv[8], bv[8], o[8];
+      unpack(ldg_vec(w + c * 8), wv);
+      if (b != nullptr) {
+        unpack(ldg_vec(b + c * 8), bv);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bv[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * wv[j] + bv[j];
+      stg_vec(y + row * cols + c * 8, pack(o));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RoPE
+// ---------------------------------------------------------------------------------------------
+__global__ void rope_table_kernel(const int64_t* __restrict__ pos, const float* __restrict__ inv_freq,
+                                  __nv_bfloat16* __restrict__ cos_o, __nv_bfloat16* __restrict__ sin_o, int64_t n,
+                                  int dim) {
+  const int half = dim / 2;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * half) return;
+  const int64_t i = idx / half;
+  const int j = (int)(idx % half);
+  // torch.outer(seq, inv_freq) in fp32 (rotary_pos_embedding.py:100), then cos/sin in fp32 and a
+  // cast to bf16 (:200-201).
+  const float ang = (float)pos[i] * inv_freq[j];
+  float sv, cv;
+  sincosf(ang, &sv, &cv);
+  const __nv_bfloat16 c = __float2bfloat16_rn(cv), s = __float2bfloat16_rn(sv);
+  cos_o[i * dim + j] = c;
+  cos_o[i * dim + half + j] = c;
+  sin_o[i * dim + j] = s;
+  sin_o[i * dim + half + j] = s;
+}
+
+// one thread: 8 elements of the first half and the matching 8 of the second half
+__global__ void __launch_bounds__(256) rope_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                   const __nv_bfloat16* __restrict__ cos_t,
+                                                   const __nv_bfloat16* __restrict__ sin_t, int64_t n_tok, int heads,
+                                                   int dim, int64_t xts, int64_t xhs, int64_t ots, int64_t ohs) {
+  const int vph = dim / 16;  // vectors (of 8) per half
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = n_tok * heads * vph;
+  if (idx >= total) return;
+  const int vi = (int)(idx % vph);
+  const int h = (int)((idx / vph) % heads);
+  const int64_t tok = idx / ((int64_t)vph * heads);
+  const int half = dim / 2;
+  const __nv_bfloat16* xp = x + tok * xts + (int64_t)h * xhs + vi * 8;
+  float x1[8], x2[8], c1[8], c2[8], s1[8], s2[8], o1[8], o2[8];
+  unpack(ldg_vec(xp), x1);
+  unpack(ldg_vec(xp + half), x2);
+  unpack(ldg_vec(cos_t + tok * dim + vi * 8), c1);
+  unpack(ldg_vec(cos_t + tok * dim + half + vi * 8), c2);
+  unpack(ldg_vec(sin_t + tok * dim + vi * 8), s1);
+  unpack(ldg_vec(sin_t + tok * dim + half + vi * 8), s2);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    // (t * cos) + (rotate_half(t) * sin), each product and the sum rounded to bf16
+    o1[j] = bf16r(x1[j] * c1[j]) + bf16r(-x2[j] * s1[j]);
+    o2[j] = bf16r(x2[j] * c2[j]) + bf16r(x1[j] * s2[j]);
+  }
+  __nv_bfloat16* op = out + tok * ots + (int64_t)h * ohs + vi * 8;
+  stg_vec(op, pack(o1));
+  stg_vec(op + half, pack(o2));
+}
+
+// ---------------------------------------------------------------------------------------------
+// SwiGLU, bias+GELU, layer-scale residual
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) swiglu_kernel(const __nv_bfloat16* __restrict__ gu,
+                                                     __nv_bfloat16* __restrict__ out, int64_t rows, int64_t inter) {
+  const int64_t vpr = inter / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * vpr) return;
+  const int64_t r = idx / vpr, c = idx % vpr;
+  float g[8], u[8], o[8];
+  unpack(ldg_stream(gu + r * 2 * inter + c * 8), g);
+  unpack(ldg_stream(gu + r * 2 * inter + inter + c * 8), u);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = bf16r(g[j] / (1.f + expf(-g[j]))) * u[j];
+  stg_vec(out + r * inter + c * 8, pack(o));
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k = 0.7978845608028654f;
+  return 0.5f * x * (1.f + tanhf(k * (x + 0.044715f * x * x * x)));
+}
+
+__global__ void __launch_bounds__(256) bias_gelu_kernel(const __nv_bfloat16* __restrict__ x,
+                                                        const __nv_bfloat16* __restrict__ bias,
+                                                        __nv_bfloat16* __restrict__ y, int64_t rows, int64_t cols,
+                                                        int approx) {
+  const int64_t vpr = cols / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * vpr) return;
+  const int64_t c = idx % vpr;
+  float v[8], o[8];
+  unpack(ldg_stream(x + idx * 8), v);
+  if (bias != nullptr) {
+    float b[8];
+    unpack(ldg_vec(bias + c * 8), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = bf16r(v[j] + b[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = approx ? gelu_tanh(v[j]) : gelu_erf(v[j]);
+  stg_vec(y + idx * 8, pack(o));
+}
+
+__global__ void __launch_bounds__(256) ls_residual_kernel(const __nv_bfloat16* __restrict__ x,
+                                                          const __nv_bfloat16* __restrict__ y,
+                                                          const __nv_bfloat16* __restrict__ bias,
+                                                          const __nv_bfloat16* __restrict__ ls,
+                                                          __nv_bfloat16* __restrict__ out, int64_t rows,
+                                                          int64_t cols) {
+  const int64_t vpr = cols / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * vpr) return;
+  const int64_t c = idx % vpr;
+  float xv[8], yv[8], o[8];
+  unpack(ldg_stream(x + idx * 8), xv);
+  unpack(ldg_stream(y + idx * 8), yv);
+  if (bias != nullptr) {
+    float b[8];
+    unpack(ldg_vec(bias + c * 8), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) yv[j] = bf16r(yv[j] + b[j]);
+  }
+  if (ls != nullptr) {
+    float l[8];
+    unpack(ldg_vec(ls + c * 8), l);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) yv[j] = bf16r(yv[j] * l[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = xv[j] + yv[j];
+  stg_vec(out + idx * 8, pack(o));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pixel shuffle (x0.5): out[n, w2*(hw/2)+h2, wi*2c + hi*c + cc] = x[n, cls + (2*w2+wi)*hw + 2*h2+hi, cc]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pixel_shuffle_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            __nv_bfloat16* __restrict__ out, int64_t n, int hw, int c,
+                                                            int has_cls) {
+  const int h2n = hw / 2;
+  const int64_t otok = blockIdx.x;  // n * h2n * h2n output tokens
+  const int64_t img = otok / (h2n * h2n);
+  const int rem = (int)(otok % (h2n * h2n));
+  const int w2 = rem / h2n, h2 = rem % h2n;
+  const int64_t in_tok_per_img = (int64_t)hw * hw + (has_cls ? 1 : 0);
+  const int vpc = c / 8;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int wi = q >> 1, hi = q & 1;
+    const int64_t itok = img * in_tok_per_img + (has_cls ? 1 : 0) + (int64_t)(2 * w2 + wi) * hw + (2 * h2 + hi);
+    const __nv_bfloat16* src = x + itok * c;
+    __nv_bfloat16* dst = out + otok * 4 * c + (int64_t)q * c;
+    for (int v = threadIdx.x; v < vpc; v += blockDim.x) stg_vec(dst + v * 8, ldg_stream(src + v * 8));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row gather kernels (embedding lookup, feature scatter, masked select / scatter)
+// ---------------------------------------------------------------------------------------------
+// out[dst(i), :] = src[srcrow(i), :];  srcrow(i) = src_idx ? src_idx[i] : i;  dst(i) = dst_idx ? dst_idx[i] : i
+__global__ void __launch_bounds__(128) row_copy_kernel(const __nv_bfloat16* __restrict__ src,
+                                                       const int64_t* __restrict__ src_idx,
+                                                       const int64_t* __restrict__ dst_idx,
+                                                       __nv_bfloat16* __restrict__ out, int64_t n, int64_t cols,
+                                                       int64_t src_rows, int64_t dst_rows) {
+  const int64_t i = blockIdx.x;
+  if (i >= n) return;
+  const int64_t s = src_idx ? src_idx[i] : i;
+  const int64_t d = dst_idx ? dst_idx[i] : i;
+  if (s < 0 || s >= src_rows || d < 0 || d >= dst_rows) return;  // out-of-range indices are dropped
+  const int64_t vpr = cols / 8;
+  for (int64_t v = threadIdx.x; v < vpr; v += blockDim.x) stg_vec(out + d * cols + v * 8, ldg_vec(src + s * cols + v * 8));
+}
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace lv
+
+using namespace lv;
+
+#define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+#define BFM(p) reinterpret_cast<__nv_bfloat16*>(p)
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" {
+
+int lv_rmsnorm(const void* x, const void* residual, const void* w, void* y, void* sum_out, int64_t rows,
+               int64_t cols, float eps, lv_stream_t stream) {
+  LV_CHECK_ARG(x && w && y, "lv_rmsnorm: null pointer");
+  LV_CHECK_ARG(rows >= 0 && cols > 0 && cols % 8 == 0 && cols <= 16384, "lv_rmsnorm: cols=%lld must be a multiple of 8 and <= 16384", (long long)cols);
+  LV_CHECK_ARG(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(residual) && aligned16(sum_out), "lv_rmsnorm: pointers must be 16-byte aligned");
+  if (rows == 0) return LV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nvec = (int)(cols / 8);
+#define LAUNCH_RMS(TPR, VPT)                                                                                   \
+  rmsnorm_kernel<TPR, VPT><<<(unsigned)cdiv(rows, 256 / TPR), 256, 0, s>>>(BF(x), BF(residual), BF(w), BFM(y), \
+                                                                           BFM(sum_out), rows, (int)cols, eps)
+  if (nvec <= 32 * 4)
+    LAUNCH_RMS(32, 4);
+  else if (nvec <= 128 * 4)
+    LAUNCH_RMS(128, 4);
+  else if (nvec <= 128 * 5)
+    LAUNCH_RMS(128, 5);
+  else
+    LAUNCH_RMS(256, 8);
+#undef LAUNCH_RMS
+  LV_CHECK_LAUNCH("rmsnorm_kernel");
+  return LV_OK;
+}
+
+int lv_layernorm(const void* x, const void* w, const void* b, void* y, int64_t rows, int64_t cols, float eps,
+                 lv_stream_t stream) {
+  LV_CHECK_ARG(x && w && y, "lv_layernorm: null pointer");
+  LV_CHECK_ARG(rows >= 0 && cols > 0 && cols % 8 == 0 && cols <= 16384, "lv_layernorm: cols=%lld must be a multiple of 8 and <= 16384", (long long)cols);
+  LV_CHECK_ARG(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(b), "lv_layernorm: pointers must be 16-byte aligned");
+  if (rows == 0) return LV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nvec = (int)(cols / 8);
+#define LAUNCH_LN(TPR, VPT) \
+  layernorm_kernel<TPR, VPT><<<(unsigned)cdiv(rows, 256 / TPR), 256, 0, s>>>(BF(x), BF(w), BF(b), BFM(y), rows, (int)cols, eps)
+  if (nvec <= 32 * 4)
+    LAUNCH_LN(32, 4);
+  else if (nvec <= 128 * 4)
+    LAUNCH_LN(128, 4);
+  else if (nvec <= 128 * 5)
+    LAUNCH_LN(128, 5);
+  else
+    LAUNCH_LN(256, 8);
+#undef LAUNCH_LN
+  LV_CHECK_LAUNCH("layernorm_kernel");
+  return LV_OK;
+}
+
+int lv_rope_table(const int64_t* pos, const float* inv_freq, void* cos_out, void* sin_out, int64_t n, int64_t dim,
+                  lv_stream_t stream) {
+  LV_CHECK_ARG(pos && inv_freq && cos_out && sin_out, "lv_rope_table: null pointer");
+  LV_CHECK_ARG(n >= 0 && dim > 0 && dim % 2 == 0, "lv_rope_table: bad dim %lld", (long long)dim);
+  if (n == 0) return LV_OK;
+  const int64_t total = n * (dim / 2);
+  rope_table_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(pos, inv_freq, BFM(cos_out),
+                                                                                 BFM(sin_out), n, (int)dim);
+  LV_CHECK_LAUNCH("rope_table_kernel");
+  return LV_OK;
+}
+
+int lv_rope(const void* x, void* out, const void* cos_t, const void* sin_t, int64_t n_tok, int64_t heads, int64_t dim,
+            int64_t x_tok_stride, int64_t x_head_stride, int64_t o_tok_stride, int64_t o_head_stride,
+            lv_stream_t stream) {
+  LV_CHECK_ARG(x && out && cos_t && sin_t, "lv_rope: null pointer");
+  LV_CHECK_ARG(dim > 0 && dim % 16 == 0, "lv_rope: dim=%lld must be a multiple of 16", (long long)dim);
+  LV_CHECK_ARG(x_tok_stride % 8 == 0 && x_head_stride % 8 == 0 && o_tok_stride % 8 == 0 && o_head_stride % 8 == 0,
+               "lv_rope: strides must be multiples of 8 elements");
+  LV_CHECK_ARG(aligned16(x) && aligned16(out) && aligned16(cos_t) && aligned16(sin_t), "lv_rope: pointers must be 16-byte aligned");
+  if (n_tok == 0 || heads == 0) return LV_OK;
+  const int64_t total = n_tok * heads * (dim / 16);
+  rope_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(BF(x), BFM(out), BF(cos_t), BF(sin_t), n_tok,
+                                                                           (int)heads, (int)dim, x_tok_stride,
+                                                                           x_head_stride, o_tok_stride, o_head_stride);
+  LV_CHECK_LAUNCH("rope_kernel");
+  return LV_OK;
+}
+
+int lv_swiglu(const void* gate_up, void* out, int64_t rows, int64_t inter, lv_stream_t stream) {
+  LV_CHECK_ARG(gate_up && out, "lv_swiglu: null pointer");
+  LV_CHECK_ARG(inter > 0 && inter % 8 == 0, "lv_swiglu: inter=%lld must be a multiple of 8", (long long)inter);
+  LV_CHECK_ARG(aligned16(gate_up) && aligned16(out), "lv_swiglu: pointers must be 16-byte aligned");
+  if (rows == 0) return LV_OK;
+  const int64_t total = rows * (inter / 8);
+  swiglu_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(BF(gate_up), BFM(out), rows, inter);
+  LV_CHECK_LAUNCH("swiglu_kernel");
+  return LV_OK;
+}
+
+int lv_bias_gelu(const void* x, const void* bias, void* y, int64_t rows, int64_t cols, int32_t approx,
+                 lv_stream_t stream) {
+  LV_CHECK_ARG(x && y, "lv_bias_gelu: null pointer");
+  LV_CHECK_ARG(cols > 0 && cols % 8 == 0, "lv_bias_gelu: cols=%lld must be a multiple of 8", (long long)cols);
+  LV_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(bias), "lv_bias_gelu: pointers must be 16-byte aligned");
+  if (rows == 0) return LV_OK;
+  const int64_t total = rows * (cols / 8);
+  bias_gelu_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(BF(x), BF(bias), BFM(y), rows, cols,
+                                                                                approx);
+  LV_CHECK_LAUNCH("bias_gelu_kernel");
+  return LV_OK;
+}
+
+int lv_ls_residual(const void* x, const void* y, const void* bias, const void* ls, void* out, int64_t rows,
+                   int64_t cols, lv_stream_t stream) {
+  LV_CHECK_ARG(x && y && out, "lv_ls_residual: null pointer");
+  LV_CHECK_ARG(cols > 0 && cols % 8 == 0, "lv_ls_residual: cols=%lld must be a multiple of 8", (long long)cols);
+  LV_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(out) && aligned16(bias) && aligned16(ls), "lv_ls_residual: pointers must be 16-byte aligned");
+  if (rows == 0) return LV_OK;
+  const int64_t total = rows * (cols / 8);
+  ls_residual_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(BF(x), BF(y), BF(bias), BF(ls),
+                                                                                  BFM(out), rows, cols);
+  LV_CHECK_LAUNCH("ls_residual_kernel");
+  return LV_OK;
+}
+
+int lv_pixel_shuffle(const void* x, void* out, int64_t n, int64_t hw, int64_t c, int32_t has_cls, lv_stream_t stream) {
+  LV_CHECK_ARG(x && out, "lv_pixel_shuffle: null pointer");
+  LV_CHECK_ARG(hw > 0 && hw % 2 == 0 && c > 0 && c % 8 == 0, "lv_pixel_shuffle: hw=%lld must be even, c=%lld a multiple of 8", (long long)hw, (long long)c);
+  LV_CHECK_ARG(aligned16(x) && aligned16(out), "lv_pixel_shuffle: pointers must be 16-byte aligned");
+  if (n == 0) return LV_OK;
+  const int64_t otoks = n * (hw / 2) * (hw / 2);
+  LV_CHECK_ARG(otoks < (1ll << 31), "lv_pixel_shuffle: too many tokens");
+  pixel_shuffle_kernel<<<(unsigned)otoks, 128, 0, (cudaStream_t)stream>>>(BF(x), BFM(out), n, (int)hw, (int)c, has_cls);
+  LV_CHECK_LAUNCH("pixel_shuffle_kernel");
+  return LV_OK;
+}
+
+int lv_embed_scatter(const int64_t* ids, const void* table, int64_t vocab, const void* feat, const int64_t* src_idx,
+                     const int64_t* dst_idx, int64_t n_scatter, void* out, int64_t n_tok, int64_t hidden,
+                     lv_stream_t stream) {
+  LV_CHECK_ARG(ids && table && out, "lv_embed_scatter: null pointer");
+  LV_CHECK_ARG(hidden > 0 && hidden % 8 == 0, "lv_embed_scatter: hidden=%lld must be a multiple of 8", (long long)hidden);
+  LV_CHECK_ARG(n_scatter == 0 || (feat && dst_idx), "lv_embed_scatter: feat/dst_idx required when n_scatter > 0");
+  LV_CHECK_ARG(aligned16(table) && aligned16(out) && aligned16(feat), "lv_embed_scatter: pointers must be 16-byte aligned");
+  LV_CHECK_ARG(n_tok < (1ll << 31) && n_scatter < (1ll << 31), "lv_embed_scatter: too many rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_tok > 0) {
+    row_copy_kernel<<<(unsigned)n_tok, 128, 0, s>>>(BF(table), ids, nullptr, BFM(out), n_tok, hidden, vocab, n_tok);
+    LV_CHECK_LAUNCH("row_copy_kernel(embed)");
+  }
+  if (n_scatter > 0) {
+    row_copy_kernel<<<(unsigned)n_scatter, 128, 0, s>>>(BF(feat), src_idx, dst_idx, BFM(out), n_scatter, hidden,
+                                                       (int64_t)1 << 62, n_tok);
+    LV_CHECK_LAUNCH("row_copy_kernel(scatter)");
+  }
+  return LV_OK;
+}
+
+int lv_row_gather(const void* x, const int64_t* idx, void* out, int64_t n_idx, int64_t cols, lv_stream_t stream) {
+  LV_CHECK_ARG(x && idx && out, "lv_row_gather: null pointer");
+  LV_CHECK_ARG(cols > 0 && cols % 8 == 0, "lv_row_gather: cols=%lld must be a multiple of 8", (long long)cols);
+  LV_CHECK_ARG(aligned16(x) && aligned16(out), "lv_row_gather: pointers must be 16-byte aligned");
+  LV_CHECK_ARG(n_idx < (1ll << 31), "lv_row_gather: too many rows");
+  if (n_idx == 0) return LV_OK;
+  row_copy_kernel<<<(unsigned)n_idx, 128, 0, (cudaStream_t)stream>>>(BF(x), idx, nullptr, BFM(out), n_idx, cols,
+                                                                    (int64_t)1 << 62, n_idx);
+  LV_CHECK_LAUNCH("row_copy_kernel(gather)");
+  return LV_OK;
+}
+
+int lv_row_scatter_zero(const void* x, const int64_t* idx, void* out, int64_t n_idx, int64_t n_rows_out, int64_t cols,
+                        lv_stream_t stream) {
+  LV_CHECK_ARG(x && idx && out, "lv_row_scatter_zero: null pointer");
+  LV_CHECK_ARG(cols > 0 && cols % 8 == 0, "lv_row_scatter_zero: cols=%lld must be a multiple of 8", (long long)cols);
+  LV_CHECK_ARG(aligned16(x) && aligned16(out), "lv_row_scatter_zero: pointers must be 16-byte aligned");
+  LV_CHECK_ARG(n_idx < (1ll << 31), "lv_row_scatter_zero: too many rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  LV_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)n_rows_out * cols * 2, s));
+  if (n_idx == 0) return LV_OK;
+  row_copy_kernel<<<(unsigned)n_idx, 128, 0, s>>>(BF(x), nullptr, idx, BFM(out), n_idx, cols, n_idx, n_rows_out);
+  LV_CHECK_LAUNCH("row_copy_kernel(scatter_zero)");
+  return LV_OK;
+}
+
+}  // extern "C"

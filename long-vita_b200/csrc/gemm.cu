@@ -1,0 +1,353 @@
+// Dense linear layer on the 5th-generation tensor cores:  C[M,N] = act(A[M,K] . W[N,K]^T + bias)
+//
+// Persistent, warp-specialised sm_100a kernel (one CTA per SM):
+//   warp 0     TMA producer: 128x64 A tiles and 256x64 W tiles (128-byte swizzle) into a 4-stage
+//              shared-memory ring, completion on mbarriers
+//   warp 1     tcgen05.mma issuer (single elected thread): UMMA 128x256x16, bf16 x bf16 -> fp32,
+//              accumulators in TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i
+//              overlaps the main loop of tile i+1
+//   warps 2-5  epilogue: tcgen05.ld TMEM -> registers, + bias, activation, bf16 pack, swizzled
+//              st.shared, TMA store (clips the M / N tails)
+// Tiles are rasterised in groups of 16 M-blocks so the concurrently resident tiles share A and W
+// panels in L2.
+//
+// Replaces torch.matmul / te.Linear at long_vita_megatron/core/tensor_parallel/layers.py:270,409 and
+// the nn.Linear calls of modeling_intern_vit.py:131,141,190-191 / resampler_projector.py:19-23.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace lv {
+
+constexpr int G_BM = 128, G_BN = 256, G_BK = 64, G_STAGES = 4;
+constexpr int G_A_BYTES = G_BM * G_BK * 2;          // 16 KB
+constexpr int G_B_BYTES = G_BN * G_BK * 2;          // 32 KB
+constexpr int G_C_BYTES = G_BM * 64 * 2;            // 16 KB staging per 64-column chunk
+constexpr int G_SMEM = G_STAGES * (G_A_BYTES + G_B_BYTES) + 2 * G_C_BYTES + 256 + 1024;  // + barriers + align slack
+constexpr int G_THREADS = 192;
+
+__device__ __forceinline__ float act_apply(float t, int act) {
+  if (act == 1) return 0.5f * t * (1.f + erff(t * 0.70710678118654752440f));
+  if (act == 2) {
+    const float k = 0.7978845608028654f;
+    return 0.5f * t * (1.f + tanhf(k * (t + 0.044715f * t * t * t)));
+  }
+  return t;
+}
+
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& mb, int& nb) {
+  constexpr int GM = 16;
+  const int per_group = GM * num_n;
+  const int g = tile / per_group;
+  const int first_m = g * GM;
+  const int gsz = min(num_m - first_m, GM);
+  const int r = tile % per_group;
+  mb = first_m + r % gsz;
+  nb = r / gsz;
+}
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+    gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, const __nv_bfloat16* __restrict__ bias, int M, int N,
+                     int K, int act) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + G_STAGES * G_A_BYTES;
+  uint8_t* sC = sB + G_STAGES * G_B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + 2 * G_C_BYTES);
+  uint64_t* full = bars;                  // [G_STAGES]
+  uint64_t* empty = bars + G_STAGES;      // [G_STAGES]
+  uint64_t* acc_full = bars + 2 * G_STAGES;       // [2]
+  uint64_t* acc_empty = bars + 2 * G_STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + G_BM - 1) / G_BM, num_n = (N + G_BN - 1) / G_BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + G_BK - 1) / G_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int i = 0; i < G_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int mb, nb;
+        tile_coords(tile, num_m, num_n, mb, nb);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], G_A_BYTES + G_B_BYTES);
+          tma_load_2d(sA + stage * G_A_BYTES, &tmA, &full[stage], kb * G_BK, mb * G_BM, kEvictNormal);
+          tma_load_2d(sB + stage * G_B_BYTES, &tmB, &full[stage], kb * G_BK, nb * G_BN, kEvictNormal);
+          if (++stage == G_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(G_BM, G_BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * G_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * G_A_BYTES), 16, 1024);
+          const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * G_B_BYTES), 16, 1024);
+#pragma unroll
+          for (int kk = 0; kk < G_BK / 16; ++kk)
+            umma_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == G_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------- epilogue -----------------------------------
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;          // row of the 128-row tile
+    const int epi_tid = (warp - 2) * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    uint32_t chunk_counter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int mb, nb;
+      tile_coords(tile, num_m, num_n, mb, nb);
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < G_BN / 64; ++c) {
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + as * G_BN + c * 64;
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 32, r1);
+        tmem_wait_ld();
+        if (c == G_BN / 64 - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        const int n0 = nb * G_BN + c * 64;
+        uint32_t packed[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float v0 = __uint_as_float(r0[j]), v1 = __uint_as_float(r0[j + 1]);
+          float w0 = __uint_as_float(r1[j]), w1 = __uint_as_float(r1[j + 1]);
+          if (bias != nullptr) {
+            const int ca = n0 + j, cb = n0 + 32 + j;
+            const float b0 = ca < N ? __bfloat162float(bias[ca]) : 0.f;
+            const float b1 = ca + 1 < N ? __bfloat162float(bias[ca + 1]) : 0.f;
+            const float b2 = cb < N ? __bfloat162float(bias[cb]) : 0.f;
+            const float b3 = cb + 1 < N ? __bfloat162float(bias[cb + 1]) : 0.f;
+            v0 += b0;
+            v1 += b1;
+            w0 += b2;
+            w1 += b3;
+          }
+          if (act != 0) {
+            // nn.Linear rounds its output to bf16 before the activation module sees it
+            v0 = act_apply(__bfloat162float(__float2bfloat16_rn(v0)), act);
+            v1 = act_apply(__bfloat162float(__float2bfloat16_rn(v1)), act);
+            w0 = act_apply(__bfloat162float(__float2bfloat16_rn(w0)), act);
+            w1 = act_apply(__bfloat162float(__float2bfloat16_rn(w1)), act);
+          }
+          packed[j / 2] = pack_bf16(v0, v1);
+          packed[16 + j / 2] = pack_bf16(w0, w1);
+        }
+        uint8_t* stg = sC + (chunk_counter & 1) * G_C_BYTES;
+        // the TMA store that last read this staging buffer (two chunks ago) must have drained
+        if (epi_tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4*>(stg + off) =
+              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (epi_tid == 0) {
+          tma_store_2d(&tmC, stg, n0, mb * G_BM);
+          tma_store_commit();
+        }
+        ++chunk_counter;
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    if (epi_tid == 0) tma_store_wait_all0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Patch embedding helpers: im2col of non-overlapping patches and the cls/pos epilogue.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) im2col_patch_kernel(const __nv_bfloat16* __restrict__ img,
+                                                           __nv_bfloat16* __restrict__ col, int64_t n, int size, int ps,
+                                                           int kpad) {
+  const int g = size / ps;
+  const int64_t patch = blockIdx.x;  // n * g * g
+  const int64_t im = patch / (g * g);
+  const int pr = (int)(patch % (g * g));
+  const int py = pr / g, px = pr % g;
+  const int kk = 3 * ps * ps;
+  for (int e = threadIdx.x; e < kpad; e += blockDim.x) {
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (e < kk) {
+      const int c = e / (ps * ps), ky = (e / ps) % ps, kx = e % ps;
+      v = img[((im * 3 + c) * size + (py * ps + ky)) * (int64_t)size + px * ps + kx];
+    }
+    col[patch * kpad + e] = v;
+  }
+}
+
+// out[n, 0, :] = cls + pos[0]; out[n, 1+p, :] = tmp[n*P + p, :] + pos[1+p]   (bf16 adds)
+__global__ void __launch_bounds__(128) add_cls_pos_kernel(const __nv_bfloat16* __restrict__ tmp,
+                                                          const __nv_bfloat16* __restrict__ cls,
+                                                          const __nv_bfloat16* __restrict__ pos,
+                                                          __nv_bfloat16* __restrict__ out, int64_t n, int P, int C) {
+  const int64_t tok = blockIdx.x;  // n * (P + 1)
+  const int64_t im = tok / (P + 1);
+  const int t = (int)(tok % (P + 1));
+  const __nv_bfloat16* src = t == 0 ? cls : tmp + (im * P + (t - 1)) * (int64_t)C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    out[tok * C + c] = __float2bfloat16_rn(__bfloat162float(src[c]) + __bfloat162float(pos[(int64_t)t * C + c]));
+}
+
+static int launch_gemm(const void* A, const void* W, const void* bias, void* C, int64_t M, int64_t N, int64_t K,
+                       int64_t lda, int64_t ldw, int64_t ldc, int act, cudaStream_t s) {
+  CUtensorMap tmA, tmB, tmC;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    const uint64_t str[2] = {2, (uint64_t)lda * 2};
+    const uint32_t box[2] = {G_BK, G_BM};
+    int r = encode_tmap_bf16(&tmA, A, 2, dims, str, box, true);
+    if (r) return r;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t str[2] = {2, (uint64_t)ldw * 2};
+    const uint32_t box[2] = {G_BK, G_BN};
+    int r = encode_tmap_bf16(&tmB, W, 2, dims, str, box, true);
+    if (r) return r;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    const uint64_t str[2] = {2, (uint64_t)ldc * 2};
+    const uint32_t box[2] = {64, G_BM};
+    int r = encode_tmap_bf16(&tmC, C, 2, dims, str, box, true);
+    if (r) return r;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    LV_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+    attr_set = true;
+  }
+  const int64_t tiles = ((M + G_BM - 1) / G_BM) * ((N + G_BN - 1) / G_BN);
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  gemm_bf16_kernel<<<grid, G_THREADS, G_SMEM, s>>>(tmA, tmB, tmC, reinterpret_cast<const __nv_bfloat16*>(bias), (int)M,
+                                                   (int)N, (int)K, act);
+  LV_CHECK_LAUNCH("gemm_bf16_kernel");
+  return LV_OK;
+}
+
+}  // namespace lv
+
+using namespace lv;
+
+extern "C" {
+
+int lv_gemm_bias_act(const void* A, const void* W, const void* bias, void* C, int64_t M, int64_t N, int64_t K,
+                     int64_t lda, int64_t ldw, int64_t ldc, int32_t act, lv_stream_t stream) {
+  LV_CHECK_ARG(A && W && C, "lv_gemm_bias_act: null pointer");
+  LV_CHECK_ARG(M >= 0 && N > 0 && K > 0, "lv_gemm_bias_act: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  LV_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "lv_gemm_bias_act: dimension too large");
+  LV_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "lv_gemm_bias_act: K=%lld and N=%lld must be multiples of 8", (long long)K, (long long)N);
+  LV_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0,
+               "lv_gemm_bias_act: leading dimensions must be >= the row length and multiples of 8");
+  LV_CHECK_ARG(act >= 0 && act <= 2, "lv_gemm_bias_act: unknown activation %d", act);
+  if (M == 0) return LV_OK;
+  return launch_gemm(A, W, bias, C, M, N, K, lda, ldw, ldc, act, (cudaStream_t)stream);
+}
+
+int64_t lv_patch_embed_ws_bytes(int64_t n, int64_t img, int64_t ps, int64_t C) {
+  const int64_t P = (img / ps) * (img / ps);
+  const int64_t kpad = ((3 * ps * ps + 63) / 64) * 64;
+  return n * P * (kpad + C) * 2;
+}
+
+int lv_patch_embed(const void* images, const void* W, const void* bias, const void* cls, const void* pos, void* out,
+                   void* ws, int64_t n, int64_t img, int64_t ps, int64_t C, lv_stream_t stream) {
+  LV_CHECK_ARG(images && W && cls && pos && out && ws, "lv_patch_embed: null pointer");
+  LV_CHECK_ARG(img > 0 && ps > 0 && img % ps == 0 && C % 8 == 0, "lv_patch_embed: bad geometry img=%lld ps=%lld C=%lld", (long long)img, (long long)ps, (long long)C);
+  if (n == 0) return LV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t P = (img / ps) * (img / ps);
+  const int64_t kpad = ((3 * ps * ps + 63) / 64) * 64;
+  LV_CHECK_ARG(n * (P + 1) < (1ll << 31), "lv_patch_embed: too many tokens");
+  __nv_bfloat16* col = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* tmp = col + n * P * kpad;
+  im2col_patch_kernel<<<(unsigned)(n * P), 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(images), col, n, (int)img,
+                                                       (int)ps, (int)kpad);
+  LV_CHECK_LAUNCH("im2col_patch_kernel");
+  int r = launch_gemm(col, W, bias, tmp, n * P, C, kpad, kpad, kpad, C, 0, s);
+  if (r) return r;
+  add_cls_pos_kernel<<<(unsigned)(n * (P + 1)), 128, 0, s>>>(tmp, reinterpret_cast<const __nv_bfloat16*>(cls),
+                                                           reinterpret_cast<const __nv_bfloat16*>(pos),
+                                                           reinterpret_cast<__nv_bfloat16*>(out), n, (int)P, (int)C);
+  LV_CHECK_LAUNCH("add_cls_pos_kernel");
+  return LV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,338 @@
+"""Operator layer: PyTorch tensors in / out, arithmetic in liblvb200.so through the C ABI.
+
+PyTorch is used for device memory, streams and autograd plumbing only.  Every function validates
+that its tensors are CUDA bf16 (or the stated integer / float type) and raises RuntimeError when
+the extension is missing or a call fails - there is no eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AttnParams
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda_bf16(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("long_vita_b200 operators run on CUDA tensors only (no CPU fallback)")
+        if t.dtype != torch.bfloat16:
+            raise RuntimeError(f"expected bfloat16 tensor, got {t.dtype}")
+
+
+def _need_cuda(t: torch.Tensor, dtype: torch.dtype) -> None:
+    if not t.is_cuda or t.dtype != dtype:
+        raise RuntimeError(f"expected CUDA {dtype} tensor, got {t.device} {t.dtype}")
+
+
+def launch_count() -> int:
+    """Kernels launched by liblvb200.so so far in this process."""
+    return int(_lib.lib().lv_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def attention_fwd(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    *,
+    causal: bool,
+    scale: Optional[float] = None,
+    layout: str = "bshd",
+    return_lse: bool = False,
+    q_seg_len: Optional[int] = None,
+    q_seg_pos: Optional[Tuple[int, int]] = None,
+    kv_pos0: int = 0,
+    out: Optional[torch.Tensor] = None,
+):
+    """softmax(scale * q k^T + mask) v.  `layout` names the dimension order of q/k/v and of the
+    returned tensor: "bshd" (flash-attn / HF), "sbhd" (Megatron, dot_product_attention.py:344) or
+    "bhsd" (HF AttentionInterface).  Strided views are consumed in place (no .contiguous()) as
+    long as the head dimension is contiguous and the other strides are multiples of 8 elements.
+    Returns out (same layout as q) or (out, lse[b, hq, sq] float32)."""
+    _need_cuda_bf16(q, k, v)
+    perm = {"bshd": (0, 1, 2, 3), "sbhd": (1, 0, 2, 3), "bhsd": (0, 2, 1, 3)}[layout]
+    qv, kv_, vv = (t.permute(perm) for t in (q, k, v))  # views in b, s, h, d order
+    b, sq, hq, d = qv.shape
+    _, sk, hkv, _ = kv_.shape
+
+    def ok(t):
+        return t.stride(3) == 1 and all(s % 8 == 0 for s in t.stride()[:3])
+
+    if not ok(qv):
+        qv = qv.contiguous()
+    if not ok(kv_):
+        kv_ = kv_.contiguous()
+    if not ok(vv):
+        vv = vv.contiguous()
+    if out is None:
+        # allocate in the caller's layout so the result is contiguous there
+        out = torch.empty(q.shape, dtype=torch.bfloat16, device=q.device)
+    ov = out.permute(perm)
+    lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device) if return_lse else None
+
+    p = AttnParams()
+    p.q, p.k, p.v, p.out = qv.data_ptr(), kv_.data_ptr(), vv.data_ptr(), ov.data_ptr()
+    p.lse = _ptr(lse)
+    p.batch, p.sq, p.sk, p.hq, p.hkv, p.d = b, sq, sk, hq, hkv, d
+    for name, t in (("q_strides", qv), ("k_strides", kv_), ("v_strides", vv), ("o_strides", ov)):
+        arr = getattr(p, name)
+        arr[0], arr[1], arr[2] = t.stride(0), t.stride(1), t.stride(2)
+    p.scale = float(scale if scale is not None else 1.0 / math.sqrt(d))
+    p.causal = 1 if causal else 0
+    p.q_seg_len = int(q_seg_len if q_seg_len is not None else sq)
+    if q_seg_pos is None:
+        q_seg_pos = (sk - sq, 0)  # bottom-right aligned causal mask (flash-attn >= 2.1)
+    p.q_seg_pos[0], p.q_seg_pos[1] = int(q_seg_pos[0]), int(q_seg_pos[1])
+    p.kv_pos0 = int(kv_pos0)
+    _lib.check(_lib.lib().lv_attn_fwd(C.byref(p), _stream()), "lv_attn_fwd")
+    return (out, lse) if return_lse else out
+
+
+# ------------------------------------------------------------------------------------------------
+# token-wise operators
+# ------------------------------------------------------------------------------------------------
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6, residual: Optional[torch.Tensor] = None):
+    """RMSNorm over the last dim.  With `residual`, returns (norm(x + residual), x + residual)."""
+    _need_cuda_bf16(x, weight, residual)
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    y = torch.empty_like(x2)
+    res2 = None
+    s = None
+    if residual is not None:
+        res2 = residual.reshape(-1, x.shape[-1]).contiguous()
+        s = torch.empty_like(x2)
+    _lib.check(
+        _lib.lib().lv_rmsnorm(x2.data_ptr(), _ptr(res2), weight.data_ptr(), y.data_ptr(), _ptr(s), x2.shape[0],
+                              x2.shape[1], float(eps), _stream()),
+        "lv_rmsnorm",
+    )
+    if residual is not None:
+        return y.view(x.shape), s.view(x.shape)
+    return y.view(x.shape)
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float = 1e-6):
+    _need_cuda_bf16(x, weight, bias)
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    y = torch.empty_like(x2)
+    _lib.check(
+        _lib.lib().lv_layernorm(x2.data_ptr(), weight.data_ptr(), _ptr(bias), y.data_ptr(), x2.shape[0], x2.shape[1],
+                                float(eps), _stream()),
+        "lv_layernorm",
+    )
+    return y.view(x.shape)
+
+
+def rope_table(pos: torch.Tensor, inv_freq: torch.Tensor):
+    """cos, sin tables (bf16 [n, 2 * len(inv_freq)]) for int64 positions `pos` [n]."""
+    _need_cuda(pos, torch.int64)
+    _need_cuda(inv_freq, torch.float32)
+    pos = pos.contiguous().view(-1)
+    dim = 2 * inv_freq.numel()
+    cos = torch.empty((pos.numel(), dim), dtype=torch.bfloat16, device=pos.device)
+    sin = torch.empty_like(cos)
+    _lib.check(
+        _lib.lib().lv_rope_table(pos.data_ptr(), inv_freq.contiguous().data_ptr(), cos.data_ptr(), sin.data_ptr(),
+                                 pos.numel(), dim, _stream()),
+        "lv_rope_table",
+    )
+    return cos, sin
+
+
+def rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """Rotate-half RoPE of x[n_tok, heads, dim] (a strided view is fine); returns a new tensor or
+    writes `out` (which may be x itself)."""
+    _need_cuda_bf16(x, cos, sin)
+    assert x.dim() == 3 and x.stride(2) == 1
+    n_tok, heads, dim = x.shape
+    if out is None:
+        out = torch.empty((n_tok, heads, dim), dtype=torch.bfloat16, device=x.device)
+    assert out.stride(2) == 1
+    _lib.check(
+        _lib.lib().lv_rope(x.data_ptr(), out.data_ptr(), cos.data_ptr(), sin.data_ptr(), n_tok, heads, dim, x.stride(0),
+                           x.stride(1), out.stride(0), out.stride(1), _stream()),
+        "lv_rope",
+    )
+    return out
+
+
+def swiglu(gate_up: torch.Tensor):
+    _need_cuda_bf16(gate_up)
+    inter = gate_up.shape[-1] // 2
+    g2 = gate_up.reshape(-1, 2 * inter)
+    if not g2.is_contiguous():
+        g2 = g2.contiguous()
+    out = torch.empty((g2.shape[0], inter), dtype=torch.bfloat16, device=gate_up.device)
+    _lib.check(_lib.lib().lv_swiglu(g2.data_ptr(), out.data_ptr(), g2.shape[0], inter, _stream()), "lv_swiglu")
+    return out.view(*gate_up.shape[:-1], inter)
+
+
+def bias_gelu(x: torch.Tensor, bias: Optional[torch.Tensor] = None, approximate: str = "none"):
+    _need_cuda_bf16(x, bias)
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    y = torch.empty_like(x2)
+    _lib.check(
+        _lib.lib().lv_bias_gelu(x2.data_ptr(), _ptr(bias), y.data_ptr(), x2.shape[0], x2.shape[1],
+                                1 if approximate == "tanh" else 0, _stream()),
+        "lv_bias_gelu",
+    )
+    return y.view(x.shape)
+
+
+def ls_residual(x: torch.Tensor, y: torch.Tensor, ls: Optional[torch.Tensor] = None,
+                bias: Optional[torch.Tensor] = None):
+    """x + (y + bias) * ls (layer-scale residual); ls / bias optional."""
+    _need_cuda_bf16(x, y, ls, bias)
+    x2 = x.reshape(-1, x.shape[-1]).contiguous()
+    y2 = y.reshape(-1, x.shape[-1]).contiguous()
+    out = torch.empty_like(x2)
+    _lib.check(
+        _lib.lib().lv_ls_residual(x2.data_ptr(), y2.data_ptr(), _ptr(bias), _ptr(ls), out.data_ptr(), x2.shape[0],
+                                  x2.shape[1], _stream()),
+        "lv_ls_residual",
+    )
+    return out.view(x.shape)
+
+
+def pixel_shuffle(x: torch.Tensor, hw: int, has_cls: bool):
+    """[n, (1 +) hw*hw, c] -> [n, (hw/2)^2, 4c]."""
+    _need_cuda_bf16(x)
+    x = x.contiguous()
+    n, _, c = x.shape
+    out = torch.empty((n, (hw // 2) ** 2, 4 * c), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().lv_pixel_shuffle(x.data_ptr(), out.data_ptr(), n, hw, c, 1 if has_cls else 0, _stream()),
+               "lv_pixel_shuffle")
+    return out
+
+
+def embed_scatter(ids: torch.Tensor, table: torch.Tensor, feat: Optional[torch.Tensor] = None,
+                  dst_idx: Optional[torch.Tensor] = None, src_idx: Optional[torch.Tensor] = None):
+    """out[t] = table[ids[t]]; out[dst_idx[i]] = feat[src_idx[i]] (src_idx None => i)."""
+    _need_cuda(ids, torch.int64)
+    _need_cuda_bf16(table, feat)
+    ids = ids.contiguous().view(-1)
+    n_tok, hidden = ids.numel(), table.shape[1]
+    out = torch.empty((n_tok, hidden), dtype=torch.bfloat16, device=table.device)
+    n_sc = 0
+    if feat is not None:
+        feat = feat.reshape(-1, hidden).contiguous()
+        dst_idx = dst_idx.contiguous().view(-1)
+        _need_cuda(dst_idx, torch.int64)
+        n_sc = dst_idx.numel()
+        if src_idx is not None:
+            src_idx = src_idx.contiguous().view(-1)
+            _need_cuda(src_idx, torch.int64)
+    _lib.check(
+        _lib.lib().lv_embed_scatter(ids.data_ptr(), table.data_ptr(), table.shape[0], _ptr(feat), _ptr(src_idx),
+                                    _ptr(dst_idx), n_sc, out.data_ptr(), n_tok, hidden, _stream()),
+        "lv_embed_scatter",
+    )
+    return out
+
+
+def row_gather(x: torch.Tensor, idx: torch.Tensor):
+    _need_cuda_bf16(x)
+    _need_cuda(idx, torch.int64)
+    x = x.contiguous()
+    idx = idx.contiguous().view(-1)
+    out = torch.empty((idx.numel(), x.shape[1]), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().lv_row_gather(x.data_ptr(), idx.data_ptr(), out.data_ptr(), idx.numel(), x.shape[1], _stream()),
+               "lv_row_gather")
+    return out
+
+
+def row_scatter_zero(x: torch.Tensor, idx: torch.Tensor, n_rows_out: int):
+    _need_cuda_bf16(x)
+    _need_cuda(idx, torch.int64)
+    x = x.contiguous()
+    idx = idx.contiguous().view(-1)
+    out = torch.empty((n_rows_out, x.shape[1]), dtype=torch.bfloat16, device=x.device)
+    _lib.check(
+        _lib.lib().lv_row_scatter_zero(x.data_ptr(), idx.data_ptr(), out.data_ptr(), idx.numel(), n_rows_out, x.shape[1],
+                                       _stream()),
+        "lv_row_scatter_zero",
+    )
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# dense linears
+# ------------------------------------------------------------------------------------------------
+_ACT = {None: 0, "none": 0, "gelu": 1, "gelu_tanh": 2}
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
+           out: Optional[torch.Tensor] = None):
+    """act(x @ weight.T + bias); weight is [N, K] (nn.Linear layout)."""
+    _need_cuda_bf16(x, weight, bias)
+    K = x.shape[-1]
+    N = weight.shape[0]
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1 or x2.stride(0) % 8 != 0:
+        x2 = x2.contiguous()
+    if weight.stride(1) != 1:
+        weight = weight.contiguous()
+    M = x2.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    _lib.check(
+        _lib.lib().lv_gemm_bias_act(x2.data_ptr(), weight.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, x2.stride(0),
+                                    weight.stride(0), out.stride(0), _ACT[act], _stream()),
+        "lv_gemm_bias_act",
+    )
+    return out.view(*x.shape[:-1], N)
+
+
+def patch_embed(images: torch.Tensor, w_pad: torch.Tensor, bias: Optional[torch.Tensor], cls: torch.Tensor,
+                pos: torch.Tensor, patch: int):
+    """images [n,3,S,S] -> [n, 1 + (S/patch)^2, C] (conv-as-GEMM + cls + position embedding).
+    `w_pad` is the conv weight flattened to [C, 3*patch*patch] and zero-padded to a multiple of 64."""
+    _need_cuda_bf16(images, w_pad, bias, cls, pos)
+    images = images.contiguous()
+    n, _, size, _ = images.shape
+    Cc = w_pad.shape[0]
+    P = (size // patch) ** 2
+    ws_bytes = int(_lib.lib().lv_patch_embed_ws_bytes(n, size, patch, Cc))
+    ws = torch.empty(ws_bytes // 2, dtype=torch.bfloat16, device=images.device)
+    out = torch.empty((n, P + 1, Cc), dtype=torch.bfloat16, device=images.device)
+    _lib.check(
+        _lib.lib().lv_patch_embed(images.data_ptr(), w_pad.contiguous().data_ptr(), _ptr(bias),
+                                  cls.contiguous().data_ptr(), pos.contiguous().data_ptr(), out.data_ptr(),
+                                  ws.data_ptr(), n, size, patch, Cc, _stream()),
+        "lv_patch_embed",
+    )
+    return out
+
+
+def pad_patch_weight(conv_weight: torch.Tensor) -> torch.Tensor:
+    """[C, 3, ps, ps] conv weight -> [C, Kpad] GEMM operand (one-time, at load)."""
+    Cc = conv_weight.shape[0]
+    flat = conv_weight.reshape(Cc, -1)
+    k = flat.shape[1]
+    kpad = (k + 63) // 64 * 64
+    out = torch.zeros((Cc, kpad), dtype=conv_weight.dtype, device=conv_weight.device)
+    out[:, :k] = flat
+    return out

@@ -1,0 +1,64 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, and exports every
+symbol include/lvb200.h declares (no compute calls - there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lvb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lv_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_hot_path():
+    syms = declared_symbols()
+    for must in ["lv_attn_fwd", "lv_rmsnorm", "lv_rope", "lv_swiglu", "lv_gemm_bias_act", "lv_patch_embed",
+                 "lv_embed_scatter", "lv_pixel_shuffle", "lv_row_gather", "lv_last_error"]:
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    lib = ctypes.CDLL(lib_built)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, f"liblvb200.so does not export: {missing}"
+
+
+def test_python_binding_covers_every_declared_symbol(lib_built):
+    from long_vita_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    handle = _lib.lib()
+    assert handle.lv_version() >= 1000
+    assert handle.lv_last_error() == b""
+
+
+def test_attn_params_struct_matches_header():
+    from long_vita_b200._lib import AttnParams
+
+    # 5 pointers + 6 int64 + 4*3 int64 + float + int32 + int64 + 2 int64 + int64
+    assert ctypes.sizeof(AttnParams) == 5 * 8 + 6 * 8 + 12 * 8 + 4 + 4 + 8 + 16 + 8
+
+
+def test_bad_arguments_fail_loudly_without_a_gpu(lib_built):
+    from long_vita_b200 import _lib
+
+    h = _lib.lib()
+    rc = h.lv_swiglu(None, None, 4, 16, None)
+    assert rc == -1 and b"null pointer" in h.lv_last_error()
+    rc = h.lv_gemm_bias_act(1, 1, None, 1, 4, 8, 7, 7, 7, 8, 0, None)
+    assert rc == -1 and b"multiples of 8" in h.lv_last_error()
+
+
+def test_ops_refuse_cpu_tensors(lib_built):
+    import torch
+
+    from long_vita_b200 import ops
+
+    x = torch.zeros(4, 16, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.swiglu(x)
