@@ -513,6 +513,7 @@ int lv_embed_scatter(const int64_t* ids, const void* table, int64_t vocab, const
 }
 
 int lv_row_gather(const void* x, const int64_t* idx, void* out, int64_t n_idx, int64_t cols, lv_stream_t stream) {
+  if (n_idx == 0) return LV_OK;
   LV_CHECK_ARG(x && idx && out, "lv_row_gather: null pointer");
   LV_CHECK_ARG(cols > 0 && cols % 8 == 0, "lv_row_gather: cols=%lld must be a multiple of 8", (long long)cols);
   LV_CHECK_ARG(aligned16(x) && aligned16(out), "lv_row_gather: pointers must be 16-byte aligned");
@@ -526,7 +527,7 @@ int lv_row_gather(const void* x, const int64_t* idx, void* out, int64_t n_idx, i
 
 int lv_row_scatter_zero(const void* x, const int64_t* idx, void* out, int64_t n_idx, int64_t n_rows_out, int64_t cols,
                         lv_stream_t stream) {
-  LV_CHECK_ARG(x && idx && out, "lv_row_scatter_zero: null pointer");
+  LV_CHECK_ARG(out && (n_idx == 0 || (x && idx)), "lv_row_scatter_zero: null pointer");
   LV_CHECK_ARG(cols > 0 && cols % 8 == 0, "lv_row_scatter_zero: cols=%lld must be a multiple of 8", (long long)cols);
   LV_CHECK_ARG(aligned16(x) && aligned16(out), "lv_row_scatter_zero: pointers must be 16-byte aligned");
   LV_CHECK_ARG(n_idx < (1ll << 31), "lv_row_scatter_zero: too many rows");

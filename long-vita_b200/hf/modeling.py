@@ -1,0 +1,291 @@
+"""B200-native Long-VITA forward with the reference's HF `forward()` surface.
+
+`LongVITAModel.forward` / `LongVITAForCausalLM.forward` keep the argument list of
+long_vita/models/long_vita_qwen2_intern/modeling_long_vita.py:74-89 and :238-255, and the
+composition of :90-221 (vision tower -> drop cls -> projector -> embedding gather + index_put ->
+decoder layers -> final norm) and :309-311 (lm_head over the last `num_logits_to_keep` rows).
+All arithmetic runs in liblvb200.so (long_vita_b200.ops); PyTorch holds the buffers.
+
+Prefill only: `past_key_values` / `use_cache` are accepted for signature compatibility and must be
+empty / False (the Megatron serving path of the reference re-prefills every token,
+long_vita_megatron/inference/text_generation/generation.py:127-135; a KV-cache decode path is the
+next scope row).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .. import ops
+from ..config import LongVITAConfig
+
+
+@dataclass
+class CausalLMOutput:
+    loss: Optional[torch.Tensor]
+    logits: torch.Tensor
+    past_key_values: Optional[object] = None
+    hidden_states: Optional[Tuple[torch.Tensor, ...]] = None
+    attentions: Optional[Tuple[torch.Tensor, ...]] = None
+
+    def to_tuple(self):
+        return tuple(v for v in (self.loss, self.logits, self.past_key_values, self.hidden_states) if v is not None)
+
+
+@dataclass
+class BaseOutput:
+    last_hidden_state: torch.Tensor
+    past_key_values: Optional[object] = None
+    hidden_states: Optional[Tuple[torch.Tensor, ...]] = None
+    attentions: Optional[Tuple[torch.Tensor, ...]] = None
+
+    def to_tuple(self):
+        return tuple(v for v in (self.last_hidden_state, self.past_key_values, self.hidden_states) if v is not None)
+
+    def __getitem__(self, i):
+        return self.to_tuple()[i]
+
+
+class InternVisionModel:
+    """InternViT-300M tower (modeling_intern_vit.py:298-363): patch-embed GEMM + cls + pos,
+    24 x [LN -> MHA -> *ls1 + res -> LN -> fc1 -> GELU -> fc2 -> *ls2 + res]."""
+
+    def __init__(self, cfg: LongVITAConfig, w: Dict[str, torch.Tensor], prefix: str = "model.vision_model."):
+        self.cfg = cfg.visual
+        v = self.cfg
+        e = prefix + "embeddings."
+        self.cls = w[e + "class_embedding"]
+        self.pos = w[e + "position_embedding"]
+        self.patch_w = ops.pad_patch_weight(w[e + "patch_embedding.weight"])
+        self.patch_b = w[e + "patch_embedding.bias"]
+        self.layers: List[Dict[str, torch.Tensor]] = []
+        for i in range(v.num_hidden_layers):
+            p = f"{prefix}encoder.layers.{i}."
+            self.layers.append({k[len(p):]: t for k, t in w.items() if k.startswith(p)})
+
+    def forward(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        v = self.cfg
+        n = pixel_values.shape[0]
+        C, H, D = v.hidden_size, v.num_attention_heads, v.head_dim
+        x = ops.patch_embed(pixel_values, self.patch_w, self.patch_b, self.cls, self.pos, v.patch_size)
+        S = x.shape[1]
+        x = x.view(n * S, C)
+        for L in self.layers:
+            h = ops.layernorm(x, L["norm1.weight"], L["norm1.bias"], v.layer_norm_eps)
+            qkv = ops.linear(h, L["attn.qkv.weight"], L.get("attn.qkv.bias")).view(n, S, 3, H, D)
+            # 'b s (three h d)' (modeling_intern_vit.py:165): q/k/v are strided views, consumed in place
+            att = ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], causal=False, scale=D ** -0.5)
+            o = ops.linear(att.view(n * S, C), L["attn.proj.weight"], L["attn.proj.bias"])
+            x = ops.ls_residual(x, o, L["ls1"])
+            h = ops.layernorm(x, L["norm2.weight"], L["norm2.bias"], v.layer_norm_eps)
+            f = ops.linear(h, L["mlp.fc1.weight"], L["mlp.fc1.bias"], act="gelu")
+            f = ops.linear(f, L["mlp.fc2.weight"], L["mlp.fc2.bias"])
+            x = ops.ls_residual(x, f, L["ls2"])
+        return x.view(n, S, C)
+
+    __call__ = forward
+
+
+class ResamplerProjector:
+    """drop cls -> pixel-shuffle x0.5 -> LayerNorm(4C) -> Linear(4C, C) -> GELU -> Linear(C, hidden)
+    (resampler_projector.py:26-34; the cls drop is modeling_long_vita.py:97, fused here)."""
+
+    def __init__(self, cfg: LongVITAConfig, w: Dict[str, torch.Tensor], prefix: str = "model.vision_projection."):
+        self.cfg = cfg
+        self.ln_w = w[prefix + "pre_proj_layernorm.weight"]
+        self.ln_b = w[prefix + "pre_proj_layernorm.bias"]
+        self.w0 = w[prefix + "mlp.0.weight"]
+        self.w2 = w[prefix + "mlp.2.weight"]
+
+    def forward(self, vit_out: torch.Tensor, has_cls: bool = True) -> torch.Tensor:
+        v = self.cfg.visual
+        x = ops.pixel_shuffle(vit_out, v.grid, has_cls=has_cls)
+        n, t, c4 = x.shape
+        x = ops.layernorm(x.view(n * t, c4), self.ln_w, self.ln_b, v.pre_proj_ln_eps)
+        x = ops.linear(x, self.w0, None, act="gelu")
+        x = ops.linear(x, self.w2)
+        return x.view(n, t, -1)
+
+    __call__ = forward
+
+
+class DecoderLayer:
+    """Qwen2 decoder layer (transformers Qwen2DecoderLayer, instantiated by the reference at
+    modeling_long_vita.py:57-72; mcore twin transformer_layer.py:173-257) with fused QKV and fused
+    gate|up weights (layout of tools/hf2mcore_long_vita.py:486-504)."""
+
+    def __init__(self, cfg: LongVITAConfig, w: Dict[str, torch.Tensor], i: int):
+        p = f"model.layers.{i}."
+        self.cfg = cfg
+        self.wqkv = torch.cat([w[p + "self_attn.q_proj.weight"], w[p + "self_attn.k_proj.weight"],
+                               w[p + "self_attn.v_proj.weight"]], dim=0).contiguous()
+        self.bqkv = torch.cat([w[p + "self_attn.q_proj.bias"], w[p + "self_attn.k_proj.bias"],
+                               w[p + "self_attn.v_proj.bias"]], dim=0).contiguous()
+        self.wo = w[p + "self_attn.o_proj.weight"]
+        self.w_gate_up = torch.cat([w[p + "mlp.gate_proj.weight"], w[p + "mlp.up_proj.weight"]], dim=0).contiguous()
+        self.w_down = w[p + "mlp.down_proj.weight"]
+        self.ln1 = w[p + "input_layernorm.weight"]
+        self.ln2 = w[p + "post_attention_layernorm.weight"]
+
+    def forward(self, x: torch.Tensor, delta: Optional[torch.Tensor], cos, sin, attn_kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+        """x [T, H] residual stream, `delta` the previous layer's MLP output not yet added
+        (the add is fused into this layer's first RMSNorm).  Returns (x, delta)."""
+        cfg = self.cfg
+        T = x.shape[0]
+        hq, hkv, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        if delta is None:
+            h = ops.rmsnorm(x, self.ln1, cfg.rms_norm_eps)
+        else:
+            h, x = ops.rmsnorm(delta, self.ln1, cfg.rms_norm_eps, residual=x)
+        qkv = ops.linear(h, self.wqkv, self.bqkv)                      # [T, (hq + 2 hkv) d]
+        q = qkv[:, : hq * d].view(T, hq, d)
+        k = qkv[:, hq * d : (hq + hkv) * d].view(T, hkv, d)
+        v = qkv[:, (hq + hkv) * d :].view(T, hkv, d)
+        ops.rope(q, cos, sin, out=q)
+        ops.rope(k, cos, sin, out=k)
+        att = ops.attention_fwd(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), causal=True, **attn_kwargs)
+        o = ops.linear(att.view(T, hq * d), self.wo)
+        h, x = ops.rmsnorm(o, self.ln2, cfg.rms_norm_eps, residual=x)
+        a = ops.swiglu(ops.linear(h, self.w_gate_up))
+        return x, ops.linear(a, self.w_down)
+
+
+class LongVITAModel:
+    def __init__(self, cfg: LongVITAConfig, weights: Dict[str, torch.Tensor]):
+        self.config = cfg
+        self.embed_tokens = weights["model.embed_tokens.weight"]
+        self.norm_w = weights["model.norm.weight"]
+        self.layers = [DecoderLayer(cfg, weights, i) for i in range(cfg.num_hidden_layers)]
+        has_vit = "model.vision_model.embeddings.class_embedding" in weights
+        self.vision_model = InternVisionModel(cfg, weights) if has_vit else None
+        self.vision_projection = ResamplerProjector(cfg, weights) if has_vit else None
+        self.inv_freq = (1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.int64).float()
+                                                    / cfg.head_dim))).to(self.embed_tokens.device)
+        self.vision_chunk = 256  # frames per ViT pass (pretrain_long_vita.py:522-533)
+
+    def encode_images(self, images: torch.Tensor) -> torch.Tensor:
+        feats = []
+        for i in range(0, images.shape[0], self.vision_chunk):
+            vit = self.vision_model(images[i : i + self.vision_chunk])
+            feats.append(self.vision_projection(vit, has_cls=True))
+        return feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
+
+    def forward(
+        self,
+        input_ids: Optional[torch.Tensor] = None,
+        attention_mask: Optional[torch.Tensor] = None,
+        images: Optional[torch.Tensor] = None,
+        image_indices: Optional[torch.Tensor] = None,
+        position_ids: Optional[torch.Tensor] = None,
+        past_key_values=None,
+        inputs_embeds: Optional[torch.Tensor] = None,
+        use_cache: Optional[bool] = None,
+        output_attentions: Optional[bool] = None,
+        output_hidden_states: Optional[bool] = None,
+        return_dict: Optional[bool] = None,
+        cache_position: Optional[torch.Tensor] = None,
+        **flash_attn_kwargs,
+    ):
+        cfg = self.config
+        if (input_ids is None) ^ (inputs_embeds is not None):
+            raise ValueError("You must specify exactly one of input_ids or inputs_embeds")
+        if past_key_values is not None and len(past_key_values) != 0:
+            raise NotImplementedError("KV-cache decode is out of this build's scope (prefill forward only)")
+        if use_cache:
+            raise NotImplementedError("use_cache=True is not supported (prefill forward only)")
+        if output_attentions:
+            raise NotImplementedError("attention probabilities are never materialised by the fused kernel")
+        if attention_mask is not None and not bool(attention_mask.to(torch.bool).all()):
+            raise NotImplementedError("padding masks are not supported; pass unpadded sequences (batch 1)")
+
+        image_embeds = None
+        if images is not None:
+            image_embeds = self.encode_images(images)
+            assert image_embeds.shape[0] == len(images)
+
+        if inputs_embeds is None:
+            b, s = input_ids.shape
+            if b != 1:
+                raise NotImplementedError("batch size 1 (the reference's long-context configuration)")
+            if image_embeds is not None:
+                idx_b, idx_s = image_indices.to(input_ids.device).unbind(dim=0)
+                dst = (idx_b.reshape(-1) * s + idx_s.reshape(-1)).to(torch.int64)
+                x = ops.embed_scatter(input_ids, self.embed_tokens, image_embeds, dst)
+            else:
+                x = ops.embed_scatter(input_ids, self.embed_tokens)
+        else:
+            b, s, _ = inputs_embeds.shape
+            if b != 1:
+                raise NotImplementedError("batch size 1")
+            x = inputs_embeds.reshape(s, -1).contiguous()
+
+        if cache_position is None:
+            cache_position = torch.arange(0, s, device=x.device)
+        if position_ids is None:
+            position_ids = cache_position.unsqueeze(0)
+        cos, sin = ops.rope_table(position_ids.reshape(-1).to(torch.int64), self.inv_freq)
+
+        all_hidden = () if output_hidden_states else None
+        delta = None
+        for layer in self.layers:
+            if output_hidden_states:
+                all_hidden += ((x if delta is None else x + delta).view(1, s, -1),)
+            x, delta = layer.forward(x, delta, cos, sin, {})
+        if delta is None:
+            h = ops.rmsnorm(x, self.norm_w, cfg.rms_norm_eps)
+        else:
+            h, _ = ops.rmsnorm(delta, self.norm_w, cfg.rms_norm_eps, residual=x)
+        h = h.view(1, s, -1)
+        if output_hidden_states:
+            all_hidden += (h,)
+        out = BaseOutput(last_hidden_state=h, past_key_values=None, hidden_states=all_hidden)
+        return out if (return_dict is None or return_dict) else out.to_tuple()
+
+    __call__ = forward
+
+
+class LongVITAForCausalLM:
+    def __init__(self, cfg: LongVITAConfig, weights: Dict[str, torch.Tensor]):
+        self.config = cfg
+        self.model = LongVITAModel(cfg, weights)
+        self.lm_head = weights["lm_head.weight"]
+
+    def forward(
+        self,
+        input_ids: Optional[torch.Tensor] = None,
+        attention_mask: Optional[torch.Tensor] = None,
+        images: Optional[torch.Tensor] = None,
+        image_indices: Optional[torch.Tensor] = None,
+        position_ids: Optional[torch.Tensor] = None,
+        past_key_values=None,
+        inputs_embeds: Optional[torch.Tensor] = None,
+        labels: Optional[torch.Tensor] = None,
+        use_cache: Optional[bool] = None,
+        output_attentions: Optional[bool] = None,
+        output_hidden_states: Optional[bool] = None,
+        return_dict: Optional[bool] = None,
+        cache_position: Optional[torch.Tensor] = None,
+        num_logits_to_keep: int = 0,
+        **kwargs,
+    ):
+        outputs = self.model(
+            input_ids=input_ids, attention_mask=attention_mask, images=images, image_indices=image_indices,
+            position_ids=position_ids, past_key_values=past_key_values, inputs_embeds=inputs_embeds,
+            use_cache=use_cache, output_attentions=output_attentions, output_hidden_states=output_hidden_states,
+            return_dict=True, cache_position=cache_position, **kwargs,
+        )
+        hidden = outputs.last_hidden_state  # [1, s, H]
+        # hidden_states[:, -num_logits_to_keep:, :] (modeling_long_vita.py:311); 0 keeps every row
+        sel = hidden[:, -num_logits_to_keep:, :] if num_logits_to_keep else hidden
+        logits = ops.linear(sel.reshape(-1, sel.shape[-1]), self.lm_head).view(1, sel.shape[1], -1)
+        loss = None
+        if labels is not None:
+            # loss_function of transformers (shifted CE in fp32); host-side torch, off the hot path
+            lg = logits.float()[:, :-1].reshape(-1, logits.shape[-1])
+            loss = torch.nn.functional.cross_entropy(lg, labels[:, -logits.shape[1]:][:, 1:].reshape(-1), ignore_index=-100)
+        out = CausalLMOutput(loss=loss, logits=logits, past_key_values=None, hidden_states=outputs.hidden_states)
+        return out if (return_dict is None or return_dict) else out.to_tuple()
+
+    __call__ = forward

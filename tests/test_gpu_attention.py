@@ -1,9 +1,11 @@
 """GPU parity: fused tcgen05 attention forward through the C ABI vs the fp32 CPU oracle.
 
-Tolerance: inputs are identical bf16 tensors; the oracle accumulates in fp32.  The kernel's output
-is bf16, whose rounding alone is ~1.1e-3 relative (rms), so the output is compared with the oracle
-rounded to bf16 (rel. Frobenius <= 2e-3, which also bounds the P-in-bf16 error flash-attention has),
-and the fp32 log-sum-exp - which sees no output rounding - must agree to 1e-3 relative / 2e-3 abs."""
+Tolerance (north_star: 1e-3 relative for bf16 activations): inputs are identical bf16 tensors and the
+oracle accumulates in fp32.  The kernel's output is bf16, and rounding ANY fp32 result to bf16
+already costs ~1.13e-3 relative Frobenius error (uniform rounding, rms 2^-9/sqrt(3)), so the test
+measures the error IN EXCESS of that floor: excess = sqrt(e(ours, ref)^2 - e(bf16(ref), ref)^2)
+must be < 1e-3.  The fp32 log-sum-exp, which sees no output rounding, must agree to 1e-4 absolute
+(observed ~1e-6).  A live flash-attn 2.8 comparator bounds the same error from the other side."""
 import math
 
 import pytest
@@ -14,8 +16,15 @@ from tests.util import max_rel, randn_bf16, rel_fro, seeded
 
 pytestmark = pytest.mark.gpu
 
-TOL_OUT = 2e-3
-TOL_LSE = 2e-3
+TOL_EXCESS = 1e-3
+TOL_LSE = 1e-4
+
+
+def excess_error(out, ref32):
+    """Relative Frobenius error of `out` against the fp32 oracle beyond the bf16 output-rounding floor."""
+    e_total = rel_fro(out, ref32)
+    e_floor = rel_fro(ref32.to(torch.bfloat16), ref32)
+    return math.sqrt(max(e_total * e_total - e_floor * e_floor, 0.0)), e_total, e_floor
 
 
 @pytest.fixture(scope="module")
@@ -35,11 +44,11 @@ def check(L, b, sq, sk, hq, hkv, d, causal, seed=0, layout="bshd", **kw):
     args = {k_: v_ for k_, v_ in kw.items() if k_ in ("q_seg_len", "q_seg_pos", "kv_pos0")}
     out, lse = L.attention_fwd(qd, kd, vd, causal=causal, layout=layout, return_lse=True, **args)
     out = out.permute(perm)
-    e_out = rel_fro(out, ref.to(torch.bfloat16))
+    e_out, e_total, e_floor = excess_error(out, ref)
     finite = torch.isfinite(lse_ref)
     e_lse = float((lse.cpu()[finite] - lse_ref[finite]).abs().max())
     assert torch.equal(torch.isfinite(lse.cpu()), finite)
-    assert e_out < TOL_OUT and e_lse < TOL_LSE, (e_out, e_lse, max_rel(out, ref))
+    assert e_out < TOL_EXCESS and e_lse < TOL_LSE, (e_out, e_total, e_floor, e_lse, max_rel(out, ref))
     return e_out, e_lse
 
 
@@ -85,7 +94,7 @@ def test_attention_strided_megatron_views(L):
     kg, vg = fg[..., 5 * d : 6 * d], fg[..., 6 * d :]
     out = L.attention_fwd(qg, kg, vg, causal=True, layout="sbhd")
     ref, _ = O.attention(q.permute(1, 0, 2, 3), k.permute(1, 0, 2, 3), v.permute(1, 0, 2, 3), causal=True)
-    assert rel_fro(out.permute(1, 0, 2, 3), ref.to(torch.bfloat16)) < TOL_OUT
+    assert excess_error(out.permute(1, 0, 2, 3), ref)[0] < TOL_EXCESS
 
 
 def test_attention_zigzag_segments_match_full_sequence(L):
@@ -102,7 +111,7 @@ def test_attention_zigzag_segments_match_full_sequence(L):
         out = L.attention_fwd(ql, kd, vd, causal=True, q_seg_len=c, q_seg_pos=(r * c, (2 * cp - 1 - r) * c))
         parts.append(out.cpu())
     full = O.zigzag_unsplit(parts)
-    assert rel_fro(full, ref.to(torch.bfloat16)) < TOL_OUT
+    assert excess_error(full, ref)[0] < TOL_EXCESS
 
 
 def test_attention_large_values_lazy_rescale(L):
@@ -116,7 +125,7 @@ def test_attention_large_values_lazy_rescale(L):
     v = randn_bf16((1, sq, h, d), g)
     ref, lse_ref = O.attention(q, k, v, causal=False)
     out, lse = L.attention_fwd(q.cuda(), k.cuda(), v.cuda(), causal=False, return_lse=True)
-    assert rel_fro(out, ref.to(torch.bfloat16)) < TOL_OUT
+    assert excess_error(out, ref)[0] < TOL_EXCESS
     assert float((lse.cpu() - lse_ref).abs().max() / lse_ref.abs().max()) < 1e-3
 
 

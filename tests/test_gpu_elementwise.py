@@ -82,7 +82,11 @@ def test_bias_gelu(L, approx):
     x, b = randn_bf16((129, 4096), g, 2.0), randn_bf16((4096,), g)
     y = L.bias_gelu(x.cuda(), b.cuda(), approx)
     ref = O.bias_gelu(x, b, approx)
-    assert rel_fro(y, ref) < 1e-3 and mismatch_fraction(y, ref) < 0.01
+    # 1 + erf(x / sqrt 2) cancels catastrophically in the far negative tail (|gelu| < 1e-5 there), so
+    # libm-vs-libdevice ulp differences flip bf16 roundings of those tiny values: bound the error
+    # in norm and absolutely instead of counting flipped elements
+    assert rel_fro(y, ref) < 1e-3
+    assert float((y.float().cpu() - ref.float()).abs().max()) < 2e-2 * float(ref.float().abs().max()) * 2 ** -7
 
 
 def test_ls_residual(L):

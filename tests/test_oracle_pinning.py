@@ -1,0 +1,166 @@
+"""Pin the CPU oracle (tests are CPU-only).
+
+The reference ships no tests or golden vectors, so the oracle is pinned against
+  (1) golden outputs generated from the reference's OWN InternVisionModel / ResamplerProjector /
+      pixel_shuffle (tests/golden/make_golden.py; regenerated and compared live when
+      /root/reference is mounted),
+  (2) the installed third-party modules whose arithmetic the reference delegates to
+      (transformers Qwen2DecoderLayer / Qwen2RMSNorm / rotary embedding),
+  (3) internal identities: the zig-zag ring schedule equals full causal attention, zig-zag
+      split / unsplit round-trips, index_of_a_in_b, masked linear forward/backward vs autograd.
+"""
+import hashlib
+import os
+import sys
+
+import pytest
+import torch
+
+from long_vita_b200.config import LongVITAConfig
+from long_vita_b200.weights import synthetic_state_dict
+from oracle import model as OM
+from oracle import ops as O
+from oracle import ref_loader
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+sys.path.insert(0, GOLD)
+
+
+def _tiny_vit_weights(seed):
+    cfg = LongVITAConfig.tiny(layers=1, vit_layers=2)
+    return cfg, synthetic_state_dict(cfg, seed=seed, dtype=torch.float32, perturb=True, llm_layers=[])
+
+
+def test_vit_and_projector_match_reference_golden():
+    from make_golden import golden_images
+
+    gold = torch.load(os.path.join(GOLD, "ref_vit_tiny.pt"))
+    cfg, w = _tiny_vit_weights(gold["seed"])
+    images = golden_images(gold["seed"], cfg.visual.image_size)
+    assert hashlib.sha256(images.view(torch.int16).numpy().tobytes()).hexdigest() == gold["images_sha256"]
+    vit = OM.vit_forward(cfg, w, images.float())
+    proj = OM.projector_forward(cfg, w, vit[:, 1:, :])
+    assert torch.allclose(vit, gold["vit_out"], rtol=1e-4, atol=1e-4), float((vit - gold["vit_out"]).abs().max())
+    assert torch.allclose(proj, gold["proj_out"], rtol=1e-4, atol=1e-4)
+
+
+def test_pixel_shuffle_matches_reference_golden_bit_exact():
+    gold = torch.load(os.path.join(GOLD, "ref_pixel_shuffle.pt"))
+    assert torch.equal(O.pixel_shuffle_half(gold["x"]), gold["y"])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted (GPU box)")
+def test_live_reference_modules_agree_with_golden_files():
+    ref = ref_loader.load()
+    gold = torch.load(os.path.join(GOLD, "ref_pixel_shuffle.pt"))
+    assert torch.equal(ref.pixel_shuffle(gold["x"], 0.5), gold["y"])
+
+
+def _hf_qwen2_layer(cfg, w, i=0):
+    from transformers import Qwen2Config
+    from transformers.models.qwen2 import modeling_qwen2 as Q
+
+    hf = Qwen2Config(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+                     num_hidden_layers=1, num_attention_heads=cfg.num_attention_heads,
+                     num_key_value_heads=cfg.num_key_value_heads, rms_norm_eps=cfg.rms_norm_eps,
+                     rope_theta=cfg.rope_theta, max_position_embeddings=1 << 20, attention_dropout=0.0)
+    hf._attn_implementation = "eager"
+    layer = Q.Qwen2DecoderLayer(hf, 0).eval()
+    p = f"model.layers.{i}."
+    layer.load_state_dict({k[len(p):]: t for k, t in w.items() if k.startswith(p)}, strict=True)
+    return hf, layer, Q
+
+
+def test_decoder_layer_matches_transformers_qwen2():
+    cfg = LongVITAConfig.tiny(layers=1)
+    w = synthetic_state_dict(cfg, seed=77, dtype=torch.float32, perturb=True, vit_layers=[])
+    hf, layer, Q = _hf_qwen2_layer(cfg, w)
+    s = 96
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(s, cfg.hidden_size, generator=g)
+    pos = torch.arange(s)
+    cos, sin = O.rope_tables(pos, O.rope_inv_freq(cfg.head_dim, cfg.rope_theta), torch.float32)
+    ours = OM.decoder_layer(cfg, w, 0, x, cos, sin)
+    rot = Q.Qwen2RotaryEmbedding(hf)
+    hcos, hsin = rot(x[None], pos[None])
+    assert torch.allclose(hcos[0], cos, atol=1e-6) and torch.allclose(hsin[0], sin, atol=1e-6)
+    mask = torch.full((s, s), float("-inf")).triu(1)[None, None]
+    with torch.no_grad():
+        theirs = layer(x[None], attention_mask=mask, position_ids=pos[None], position_embeddings=(hcos, hsin))
+    theirs = theirs[0] if isinstance(theirs, tuple) else theirs
+    assert torch.allclose(ours, theirs.reshape(s, -1), rtol=1e-4, atol=1e-4), float((ours - theirs.reshape(s, -1)).abs().max())
+
+
+def test_rmsnorm_matches_transformers_bf16_bitwise():
+    from transformers.models.qwen2.modeling_qwen2 import Qwen2RMSNorm
+
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(33, 640, generator=g).to(torch.bfloat16)
+    m = Qwen2RMSNorm(640, eps=1e-6).to(torch.bfloat16)
+    m.weight.data = (1 + 0.1 * torch.randn(640, generator=g)).to(torch.bfloat16)
+    assert torch.equal(O.rmsnorm(x, m.weight.data, 1e-6), m(x))
+
+
+@pytest.mark.parametrize("cp", [2, 4, 8])
+def test_zigzag_ring_schedule_equals_full_causal_attention(cp):
+    g = torch.Generator().manual_seed(cp)
+    S, hq, hkv, d = 64 * cp, 4, 2, 32
+    q, k, v = (torch.randn(1, S, h, d, generator=g) for h in (hq, hkv, hkv))
+    ref, lse = O.attention(q, k, v, causal=True)
+    outs, lses = O.ring_attention_zigzag(q, k, v, cp)
+    full = O.zigzag_unsplit(outs)
+    full_lse = O.zigzag_unsplit([l.permute(0, 2, 1) for l in lses]).permute(0, 2, 1)
+    assert torch.allclose(full, ref, atol=2e-5) and torch.allclose(full_lse, lse, atol=2e-5)
+
+
+def test_zigzag_split_roundtrip_and_reference_formula():
+    x = torch.arange(2 * 48 * 3).reshape(2, 48, 3)
+    for cp in (1, 2, 4):
+        parts = [O.zigzag_split(x, cp, r) for r in range(cp)]
+        assert torch.equal(O.zigzag_unsplit(parts), x)
+        for r in range(cp):
+            # val.view(.., 2cp, S/2cp, ..).index_select(seq_dim, [r, 2cp-1-r]) (training/utils.py:331-341)
+            v = x.view(2, 2 * cp, 48 // (2 * cp), 3).index_select(1, torch.tensor([r, 2 * cp - 1 - r])).reshape(2, -1, 3)
+            assert torch.equal(parts[r], v)
+
+
+def test_index_of_a_in_b():
+    g = torch.Generator().manual_seed(3)
+    b = torch.randperm(1000, generator=g)[:400]
+    a = b[torch.randperm(400, generator=g)[:150]]
+    idx = O.index_of_a_in_b(a, b)
+    assert torch.equal(b[idx], a)
+    # the reference's formulation (training/utils.py:347-350)
+    b_idx = torch.where(torch.isin(b, a))[0]
+    ref = b_idx[b[b_idx].argsort()[a.argsort().argsort()]]
+    assert torch.equal(idx, ref)
+
+
+def test_masked_linear_forward_backward_match_autograd():
+    g = torch.Generator().manual_seed(4)
+    s, b, c, vocab = 40, 1, 32, 50
+    h = torch.randn(s, b, c, generator=g, requires_grad=True)
+    wt = torch.randn(vocab, c, generator=g, requires_grad=True)
+    mask = (torch.rand(b, s, generator=g) < 0.3)
+    out = O.masked_linear_fwd(h, wt, mask)
+    dense = torch.matmul(h, wt.t())[mask.transpose(0, 1)].reshape(-1, b, vocab)
+    assert torch.allclose(out, dense, atol=1e-6)
+    go = torch.randn(out.shape, generator=g)
+    out.backward(go)
+    gx, gw = O.masked_linear_bwd(go, h.detach(), wt.detach(), mask)
+    assert torch.allclose(gx, h.grad, atol=1e-5) and torch.allclose(gw, wt.grad, atol=1e-5)
+
+
+def test_whole_model_oracle_runs_and_uses_image_features():
+    cfg = LongVITAConfig.tiny(layers=2, vit_layers=1)
+    w = synthetic_state_dict(cfg, seed=9, dtype=torch.float32, perturb=True)
+    g = torch.Generator().manual_seed(1)
+    s = 300
+    ids = torch.randint(0, cfg.vocab_size, (1, s), generator=g)
+    images = torch.randn(1, 3, 448, 448, generator=g)
+    idx = torch.stack([torch.zeros(1, 256, dtype=torch.long), torch.arange(10, 266).view(1, 256)])
+    a = OM.long_vita_forward(cfg, w, ids, images, idx, num_logits_to_keep=1)
+    b = OM.long_vita_forward(cfg, w, ids, images * 0.5, idx, num_logits_to_keep=1)
+    c = OM.long_vita_forward(cfg, w, ids, None, None, num_logits_to_keep=1)
+    assert a.shape == (1, 1, cfg.vocab_size)
+    assert not torch.allclose(a, b) and not torch.allclose(a, c)
