@@ -15,7 +15,7 @@
  *     thread-local description of the last failure on the calling thread;
  *   - activations are bfloat16 unless stated otherwise ("bf16" below), statistics are float;
  *   - all functions are re-entrant and keep no mutable global state other than the
- *     once-per-process symmetric KV heap registered through lv_cp_register().
+ *     peer-mapped allocations made through lv_ipc_alloc().
  */
 #ifndef LVB200_H_
 #define LVB200_H_
@@ -79,6 +79,52 @@ typedef struct lv_attn_params {
 } lv_attn_params;
 
 int lv_attn_fwd(const lv_attn_params* p, lv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Context-parallel attention (forward): zig-zag sequence sharding with the K/V exchange inside the
+ * attention kernel.
+ *
+ * Replaces TransformerEngine's ring attention (`TEDotProductAttention` with cp_group,
+ * long_vita_megatron/core/models/gpt/gpt_layer_specs.py:35-45; un-vendored `AttnFuncWithCP`:
+ * cp steps of flash-attn on zig-zag half-chunks + NCCL P2P + LSE merge) and uses the data layout
+ * of long_vita_megatron/training/utils.py:329-341: the S-token sequence is cut into 2*cp chunks
+ * of c = S/(2 cp) tokens, rank r owns chunks {r, 2cp-1-r} (sq = 2c local rows).
+ *
+ * Every rank keeps its K|V rows (this epoch's, after RoPE) in a peer-mapped buffer obtained from
+ * lv_ipc_alloc(); `peer_kv[p]` is the (peer-mapped) address of rank p's K of local token 0, with
+ * V following K inside the row and `peer_tok_stride` elements between tokens - for the fused QKV
+ * GEMM output [T, (hq + 2 hkv) d] that is the K column of the buffer itself, so no copy precedes
+ * the exchange.  Copier warps inside the kernel wait for the owner's ready flag (system-scope
+ * acquire), pull the visible chunks over NVLink into the caller's staging buffers
+ * k_full / v_full [S, hkv*d] in global order and publish per-128-token flags the TMA producer
+ * polls; the math of already-staged blocks overlaps the transfer of later ones.  No NCCL call is
+ * on this path.  `epoch` must increase by one per call, identically on all ranks; buffers alternate
+ * by epoch parity (two K|V buffers per rank) so that no barrier is needed between layers.
+ * `a` describes the local queries against the staging buffers: k = k_full, v = v_full, sk = S,
+ * q_seg_len = c, q_seg_pos = {r c, (2cp-1-r) c}, kv_pos0 = 0, causal = 1, batch = 1, d = 128.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lv_cp_params {
+  int32_t rank, cp;          /* 2 <= cp <= 8 */
+  int64_t seq_total;         /* S */
+  uint32_t epoch;            /* call counter (same on every rank) */
+  int64_t peer_tok_stride;   /* elements */
+  const void* peer_kv[8];    /* [cp] peer-mapped K row-0 address of rank p for this epoch's parity */
+  void* peer_ready[8];       /* [cp] peer-mapped base of rank p's ready words: uint32[2][8] */
+  void* my_ready;            /* local base of the same array */
+  void* k_full;              /* bf16 [S, hkv*d] staging (local) */
+  void* v_full;
+  void* blk_flags;           /* uint32 [S/128], zero-initialised once */
+} lv_cp_params;
+
+int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv_stream_t stream);
+
+/* Peer-mappable device memory (cudaMalloc + CUDA IPC).  The 64-byte handle is exchanged by the
+ * host (torch.distributed) and opened on the other ranks of the node. */
+int lv_ipc_alloc(int64_t bytes, void** ptr);
+int lv_ipc_free(void* ptr);
+int lv_ipc_get_handle(void* ptr, void* handle64);
+int lv_ipc_open_handle(const void* handle64, void** ptr);
+int lv_ipc_close_handle(void* ptr);
 
 /* ------------------------------------------------------------------------------------------
  * Token-wise memory-bound operators (HBM roofline).

@@ -34,12 +34,28 @@ class AttnParams(C.Structure):
     ]
 
 
+class CpParams(C.Structure):
+    """Mirror of `lv_cp_params` (include/lvb200.h)."""
+
+    _fields_ = [
+        ("rank", c_i32), ("cp", c_i32), ("seq_total", c_i64), ("epoch", C.c_uint32), ("peer_tok_stride", c_i64),
+        ("peer_kv", c_ptr * 8), ("peer_ready", c_ptr * 8), ("my_ready", c_ptr),
+        ("k_full", c_ptr), ("v_full", c_ptr), ("blk_flags", c_ptr),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/lvb200.h declares
 SIGNATURES = {
     "lv_version": (c_i32, []),
     "lv_last_error": (C.c_char_p, []),
     "lv_launch_count": (c_i64, []),
     "lv_attn_fwd": (c_i32, [C.POINTER(AttnParams), c_ptr]),
+    "lv_attn_cp_fwd": (c_i32, [C.POINTER(AttnParams), C.POINTER(CpParams), c_ptr]),
+    "lv_ipc_alloc": (c_i32, [c_i64, C.POINTER(c_ptr)]),
+    "lv_ipc_free": (c_i32, [c_ptr]),
+    "lv_ipc_get_handle": (c_i32, [c_ptr, c_ptr]),
+    "lv_ipc_open_handle": (c_i32, [c_ptr, C.POINTER(c_ptr)]),
+    "lv_ipc_close_handle": (c_i32, [c_ptr]),
     "lv_rmsnorm": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_ptr]),
     "lv_layernorm": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_ptr]),
     "lv_rope_table": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr]),

@@ -24,6 +24,8 @@
 // long_vita/models/long_vita_qwen2_intern/flash_attention.py:52-74.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -44,6 +46,51 @@ struct AttnKParams {
   int n_items;     // batch * hq * n_qblk
   float* lse;
 };
+
+// Context-parallel extension (zig-zag layout, training/utils.py:329-341).  Every rank keeps its own
+// K/V rows inside a peer-mapped ("symmetric") buffer; the copier warps of this kernel pull the
+// chunks this rank's queries can see from the owning GPUs over NVLink into a local staging copy in
+// global sequence order, 128-token block by block, and publish a per-block flag the TMA producer
+// polls - so the K/V exchange is part of the attention kernel and overlaps its math.
+struct CpKParams {
+  int rank, cp;
+  int chunk;                 // tokens per zig-zag chunk: S / (2 cp)
+  int nblk_needed;           // 128-token key blocks this rank's queries can see
+  uint32_t epoch1;           // epoch + 1 (flags are monotonic, never reset)
+  int kv_row_elems;          // hkv * d
+  long long peer_tok_stride; // elements between consecutive tokens in a peer's K|V rows
+  const __nv_bfloat16* peer_kv[8];   // peer p: address of K of its local token 0 (V follows K in the row)
+  uint32_t* peer_ready[8];           // peer p: its ready[parity][my rank] word
+  const uint32_t* my_ready;          // ready[parity][0..cp)
+  __nv_bfloat16* k_full;             // staging [S, hkv*d]
+  __nv_bfloat16* v_full;
+  uint32_t* blk_flags;               // [S / 128]
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_peer_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
 
 template <int D>
 struct AttnCfg {
@@ -101,11 +148,11 @@ __device__ __forceinline__ WorkItem decode_item(const AttnKParams& p, int item) 
   return w;
 }
 
-template <int D>
+template <int D, bool PF16, bool CP>
 __global__ void __launch_bounds__(A_THREADS, 1)
     attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
-                    const AttnKParams p) {
+                    const AttnKParams p, const CpKParams cpp) {
   using Cfg = AttnCfg<D>;
   constexpr int NS = Cfg::KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -162,6 +209,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (lane == 0) {
       uint32_t item_cnt = 0, kcnt = 0, vcnt = 0;
+      int ready_upto = 0;   // CP: key blocks [0, ready_upto) are known to be staged
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
         const WorkItem w = decode_item(p, item);
         const int nmax = max(w.n[0], w.n[1]);
@@ -173,6 +221,12 @@ __global__ void __launch_bounds__(A_THREADS, 1)
                         kEvictFirst);
         }
         for (int j = 0; j < nmax; ++j) {
+          if (CP && j >= ready_upto) {
+            while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1) {
+            }
+            ready_upto = j + 1;
+            fence_proxy_async_all();   // copier warps wrote the staging rows through the generic proxy
+          }
           {
             const int st = kcnt % NS;
             mbar_wait(&k_empty[st], ((kcnt / NS) & 1) ^ 1);
@@ -199,7 +253,9 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(A_BM, A_BN, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(A_BM, D, 0, 1);
+      // P is the A operand: bf16, or fp16 (format code 0) when PF16 - kind::f16 takes the A and B
+      // element formats independently, and fp16's 11-bit mantissa removes most of the P rounding error
+      constexpr uint32_t idesc_pv = make_idesc_bf16(A_BM, D, 0, 1) & ~(PF16 ? (7u << 7) : 0u);
       const uint32_t tS[2] = {tmem_base + Cfg::TM_S0, tmem_base + Cfg::TM_S1};
       const uint32_t tO[2] = {tmem_base + Cfg::TM_O0, tmem_base + Cfg::TM_O1};
       uint32_t item_cnt = 0, kcnt = 0, vcnt_wait = 0, vcnt_rel = 0;
@@ -380,8 +436,8 @@ __global__ void __launch_bounds__(A_THREADS, 1)
             l1 += p1;
             l2 += p2;
             l3 += p3;
-            pk[i / 2] = pack_bf16(p0, p1);
-            pk[i / 2 + 1] = pack_bf16(p2, p3);
+            pk[i / 2] = PF16 ? pack_f16(p0, p1) : pack_bf16(p0, p1);
+            pk[i / 2 + 1] = PF16 ? pack_f16(p2, p3) : pack_bf16(p2, p3);
           }
           tmem_st16(tS + c * 16, pk);
         }
@@ -441,7 +497,65 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     }
     if (wg_tid == 0) tma_store_wait_all0();
   } else {
+    // =========================== warps 2-3: context-parallel K/V copier ===========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    if (CP) {
+      const int cw = blockIdx.x * 2 + (warp - 2);          // copier index
+      const int ncw = gridDim.x * 2;
+      if (cw == 0) {
+        // tell every peer that this rank's K/V rows for this epoch are complete (they were written
+        // by earlier kernels on this stream; the fence orders them before the flag at system scope)
+        __threadfence_system();
+        if (lane < cpp.cp && lane != cpp.rank) st_release_sys(cpp.peer_ready[lane], cpp.epoch1);
+      }
+      uint32_t seen = 1u << cpp.rank;                      // peers whose ready flag has been observed
+      const int vec_per_row = cpp.kv_row_elems / 4;        // 16-byte vectors in one K|V row pair
+      const int vec_per_half = cpp.kv_row_elems / 8;
+      for (int b = cw; b < cpp.nblk_needed; b += ncw) {
+        const int tok0 = b * A_BN;
+        const int chunk = tok0 / cpp.chunk;
+        const int owner = chunk < cpp.cp ? chunk : 2 * cpp.cp - 1 - chunk;
+        const int lrow0 = (chunk < cpp.cp ? 0 : cpp.chunk) + (tok0 - chunk * cpp.chunk);
+        if (!(seen & (1u << owner))) {
+          if (lane == 0)
+            while (ld_acquire_sys(cpp.my_ready + owner) < cpp.epoch1) {
+            }
+          __syncwarp();
+          seen |= 1u << owner;
+        }
+        const __nv_bfloat16* src = cpp.peer_kv[owner] + (long long)lrow0 * cpp.peer_tok_stride;
+        const int total = A_BN * vec_per_row;
+        for (int i0 = 0; i0 < total; i0 += 32 * 4) {
+          uint4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            const int row = i / vec_per_row, col = i - row * vec_per_row;
+            v[u] = ld_peer_v4(src + (long long)row * cpp.peer_tok_stride + col * 8);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            const int row = i / vec_per_row, col = i - row * vec_per_row;
+            __nv_bfloat16* dst = col < vec_per_half
+                                     ? cpp.k_full + (long long)(tok0 + row) * cpp.kv_row_elems + col * 8
+                                     : cpp.v_full + (long long)(tok0 + row) * cpp.kv_row_elems + (col - vec_per_half) * 8;
+            *reinterpret_cast<uint4*>(dst) = v[u];
+          }
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_gpu(cpp.blk_flags + b, cpp.epoch1);
+      }
+      if (cw == 0) {
+        // do not retire before every peer has entered this epoch: a peer's flag for epoch e+1 then
+        // proves it finished reading our epoch e-1 rows (buffer parity reuse)
+        if (lane < cpp.cp && lane != cpp.rank)
+          while (ld_acquire_sys(cpp.my_ready + lane) < cpp.epoch1) {
+          }
+        __syncwarp();
+      }
+    }
   }
 
   tc_fence_before();
@@ -449,8 +563,8 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int D>
-static int launch_attn(const lv_attn_params* a, cudaStream_t s) {
+template <int D, bool PF16, bool CP>
+static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_t s) {
   using Cfg = AttnCfg<D>;
   CUtensorMap tmQ, tmK, tmV, tmO;
   const uint32_t box[4] = {64, 128, 1, 1};
@@ -489,11 +603,17 @@ static int launch_attn(const lv_attn_params* a, cudaStream_t s) {
   p.lse = a->lse;
   static bool attr_set = false;
   if (!attr_set) {
-    LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
+    LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, PF16, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     attr_set = true;
   }
-  const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-  attn_fwd_kernel<D><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p);
+  int grid = p.n_items < sm_count() ? p.n_items : sm_count();
+  CpKParams cpp;
+  memset(&cpp, 0, sizeof(cpp));
+  if (CP) {
+    cpp = *cp;
+    grid = sm_count();   // every copier warp takes part, also when there are fewer work items than SMs
+  }
+  attn_fwd_kernel<D, PF16, CP><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p, cpp);
   LV_CHECK_LAUNCH("attn_fwd_kernel");
   return LV_OK;
 }
@@ -502,7 +622,7 @@ static int launch_attn(const lv_attn_params* a, cudaStream_t s) {
 
 using namespace lv;
 
-extern "C" int lv_attn_fwd(const lv_attn_params* a, lv_stream_t stream) {
+static int check_attn_params(const lv_attn_params* a) {
   LV_CHECK_ARG(a != nullptr, "lv_attn_fwd: null params");
   LV_CHECK_ARG(a->q && a->k && a->v && a->out, "lv_attn_fwd: null tensor pointer");
   LV_CHECK_ARG(a->d == 64 || a->d == 128, "lv_attn_fwd: head_dim %lld not supported (64, 128)", (long long)a->d);
@@ -517,7 +637,87 @@ extern "C" int lv_attn_fwd(const lv_attn_params* a, lv_stream_t stream) {
   for (int i = 0; i < 3; ++i)
     LV_CHECK_ARG(a->q_strides[i] % 8 == 0 && a->k_strides[i] % 8 == 0 && a->v_strides[i] % 8 == 0 && a->o_strides[i] % 8 == 0,
                  "lv_attn_fwd: strides must be multiples of 8 elements (16 bytes)");
+  return LV_OK;
+}
+
+extern "C" int lv_attn_fwd(const lv_attn_params* a, lv_stream_t stream) {
+  int rc = check_attn_params(a);
+  if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  if (a->d == 128) return launch_attn<128>(a, s);
-  return launch_attn<64>(a, s);
+  // P is bf16 like V: tcgen05 kind::f16 faults on an fp16 A operand against a bf16 B operand
+  // (measured on B200), so the fp16-P instantiation is never launched.
+  if (a->d == 128) return launch_attn<128, false, false>(a, nullptr, s);
+  return launch_attn<64, false, false>(a, nullptr, s);
+}
+
+extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv_stream_t stream) {
+  int rc = check_attn_params(a);
+  if (rc) return rc;
+  LV_CHECK_ARG(c != nullptr, "lv_attn_cp_fwd: null cp params");
+  LV_CHECK_ARG(c->cp >= 2 && c->cp <= 8 && c->rank >= 0 && c->rank < c->cp, "lv_attn_cp_fwd: bad rank %d / cp %d", c->rank, c->cp);
+  LV_CHECK_ARG(a->batch == 1 && a->causal, "lv_attn_cp_fwd: batch 1, causal only");
+  LV_CHECK_ARG(a->d == 128, "lv_attn_cp_fwd: head_dim 128 only");
+  const int64_t S = c->seq_total;
+  LV_CHECK_ARG(S % (2 * c->cp) == 0, "lv_attn_cp_fwd: seq_total %lld not divisible by 2*cp", (long long)S);
+  const int64_t chunk = S / (2 * c->cp);
+  LV_CHECK_ARG(chunk % 256 == 0, "lv_attn_cp_fwd: chunk %lld must be a multiple of 256 tokens", (long long)chunk);
+  LV_CHECK_ARG(a->sq == 2 * chunk && a->sk == S && a->q_seg_len == chunk && a->kv_pos0 == 0,
+               "lv_attn_cp_fwd: expects sq = 2*chunk local queries against the S-row staging buffers");
+  LV_CHECK_ARG(a->q_seg_pos[0] == c->rank * chunk && a->q_seg_pos[1] == (2 * c->cp - 1 - c->rank) * chunk,
+               "lv_attn_cp_fwd: q_seg_pos does not match the zig-zag layout of rank %d", c->rank);
+  LV_CHECK_ARG(a->k == c->k_full && a->v == c->v_full, "lv_attn_cp_fwd: k / v must be the staging buffers");
+  LV_CHECK_ARG(c->my_ready && c->blk_flags && c->k_full && c->v_full, "lv_attn_cp_fwd: null cp buffer");
+  CpKParams k;
+  memset(&k, 0, sizeof(k));
+  k.rank = c->rank;
+  k.cp = c->cp;
+  k.chunk = (int)chunk;
+  k.nblk_needed = (int)((2 * c->cp - c->rank) * chunk / A_BN);
+  k.epoch1 = c->epoch + 1;
+  k.kv_row_elems = (int)(a->hkv * a->d);
+  k.peer_tok_stride = c->peer_tok_stride;
+  const int parity = (int)(c->epoch & 1);
+  for (int p = 0; p < c->cp; ++p) {
+    LV_CHECK_ARG(c->peer_kv[p] != nullptr && c->peer_ready[p] != nullptr, "lv_attn_cp_fwd: null peer pointer for rank %d", p);
+    k.peer_kv[p] = reinterpret_cast<const __nv_bfloat16*>(c->peer_kv[p]);
+    k.peer_ready[p] = reinterpret_cast<uint32_t*>(c->peer_ready[p]) + parity * 8 + c->rank;
+  }
+  k.my_ready = reinterpret_cast<const uint32_t*>(c->my_ready) + parity * 8;
+  k.k_full = reinterpret_cast<__nv_bfloat16*>(c->k_full);
+  k.v_full = reinterpret_cast<__nv_bfloat16*>(c->v_full);
+  k.blk_flags = reinterpret_cast<uint32_t*>(c->blk_flags);
+  return launch_attn<128, false, true>(a, &k, (cudaStream_t)stream);
+}
+
+// Peer-mappable ("symmetric") allocations for the context-parallel K/V exchange: plain cudaMalloc
+// memory exported / imported with CUDA IPC handles (64 opaque bytes the host exchanges over
+// torch.distributed).
+extern "C" int lv_ipc_alloc(int64_t bytes, void** ptr) {
+  LV_CHECK_ARG(ptr != nullptr && bytes > 0, "lv_ipc_alloc: bad arguments");
+  LV_CHECK_CUDA(cudaMalloc(ptr, (size_t)bytes));
+  LV_CHECK_CUDA(cudaMemset(*ptr, 0, (size_t)bytes));
+  return LV_OK;
+}
+extern "C" int lv_ipc_free(void* ptr) {
+  if (ptr) LV_CHECK_CUDA(cudaFree(ptr));
+  return LV_OK;
+}
+extern "C" int lv_ipc_get_handle(void* ptr, void* handle64) {
+  LV_CHECK_ARG(ptr && handle64, "lv_ipc_get_handle: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  LV_CHECK_CUDA(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, 64);
+  return LV_OK;
+}
+extern "C" int lv_ipc_open_handle(const void* handle64, void** ptr) {
+  LV_CHECK_ARG(ptr && handle64, "lv_ipc_open_handle: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  LV_CHECK_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return LV_OK;
+}
+extern "C" int lv_ipc_close_handle(void* ptr) {
+  if (ptr) LV_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return LV_OK;
 }

@@ -252,6 +252,37 @@ class LongVITAForCausalLM:
         self.model = LongVITAModel(cfg, weights)
         self.lm_head = weights["lm_head.weight"]
 
+    @classmethod
+    def from_synthetic(cls, cfg: LongVITAConfig, seed: int = 1234, device="cuda", perturb: bool = False,
+                       num_layers: Optional[int] = None):
+        """Random-init model materialised layer by layer on `device` (14B bf16 = 29.5 GB never
+        exists twice): every decoder layer's q/k/v and gate/up matrices are fused as they are drawn."""
+        from ..weights import global_weights, llm_layer_weights, vit_layer_weights
+
+        w = global_weights(cfg, seed, device, torch.bfloat16, perturb)
+        for i in range(cfg.visual.num_hidden_layers):
+            w.update(vit_layer_weights(cfg, i, seed, device, torch.bfloat16, perturb))
+        n_layers = cfg.num_hidden_layers if num_layers is None else num_layers
+        self = cls.__new__(cls)
+        self.config = cfg
+        self.lm_head = w["lm_head.weight"]
+        model = LongVITAModel.__new__(LongVITAModel)
+        model.config = cfg
+        model.embed_tokens = w["model.embed_tokens.weight"]
+        model.norm_w = w["model.norm.weight"]
+        model.vision_model = InternVisionModel(cfg, w)
+        model.vision_projection = ResamplerProjector(cfg, w)
+        model.inv_freq = (1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.int64).float()
+                                                     / cfg.head_dim))).to(device)
+        model.vision_chunk = 256
+        model.layers = []
+        for i in range(n_layers):
+            lw = llm_layer_weights(cfg, i, seed, device, torch.bfloat16, perturb)
+            model.layers.append(DecoderLayer(cfg, lw, i))
+            del lw
+        self.model = model
+        return self
+
     def forward(
         self,
         input_ids: Optional[torch.Tensor] = None,

@@ -39,6 +39,42 @@ def _need_cuda(t: torch.Tensor, dtype: torch.dtype) -> None:
         raise RuntimeError(f"expected CUDA {dtype} tensor, got {t.device} {t.dtype}")
 
 
+class KernelTimer:
+    """Optional per-launch device timing of the two tensor-core kernels (CUDA events on the
+    launching stream).  bench.py installs one for its roofline numbers; None costs nothing."""
+
+    def __init__(self):
+        self.records = []  # (kind, algorithmic flops, start event, end event)
+
+    def start(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def stop(self, kind, flops, ev0):
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        self.records.append((kind, flops, ev0, ev1))
+
+    def summary(self):
+        """kind -> dict(launches, ms, flops); call after a synchronize."""
+        out = {}
+        for kind, flops, e0, e1 in self.records:
+            d = out.setdefault(kind, {"launches": 0, "ms": 0.0, "flops": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+        return out
+
+
+_TIMER: Optional[KernelTimer] = None
+
+
+def set_kernel_timer(t: Optional[KernelTimer]) -> None:
+    global _TIMER
+    _TIMER = t
+
+
 def launch_count() -> int:
     """Kernels launched by liblvb200.so so far in this process."""
     return int(_lib.lib().lv_launch_count())
@@ -101,7 +137,14 @@ def attention_fwd(
         q_seg_pos = (sk - sq, 0)  # bottom-right aligned causal mask (flash-attn >= 2.1)
     p.q_seg_pos[0], p.q_seg_pos[1] = int(q_seg_pos[0]), int(q_seg_pos[1])
     p.kv_pos0 = int(kv_pos0)
+    ev0 = _TIMER.start() if _TIMER is not None else None
     _lib.check(_lib.lib().lv_attn_fwd(C.byref(p), _stream()), "lv_attn_fwd")
+    if ev0 is not None:
+        if causal and q_seg_len is None and sq == sk:
+            fl = 4.0 * b * hq * d * (sq * (sq + 1) / 2)
+        else:
+            fl = 4.0 * b * hq * d * sq * sk  # upper bound for masked / segmented calls
+        _TIMER.stop("attn_fwd", fl, ev0)
     return (out, lse) if return_lse else out
 
 
@@ -298,11 +341,14 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     M = x2.shape[0]
     if out is None:
         out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    ev0 = _TIMER.start() if _TIMER is not None else None
     _lib.check(
         _lib.lib().lv_gemm_bias_act(x2.data_ptr(), weight.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, x2.stride(0),
                                     weight.stride(0), out.stride(0), _ACT[act], _stream()),
         "lv_gemm_bias_act",
     )
+    if ev0 is not None:
+        _TIMER.stop("gemm_bf16", 2.0 * M * N * K, ev0)
     return out.view(*x.shape[:-1], N)
 
 

@@ -1,0 +1,83 @@
+"""Multi-GPU parity of the fused context-parallel attention (in-kernel K/V exchange over NVLink)
+and of the sharded prefill: cp = N ranks must reproduce the single-device result (the invariant
+TE / ring-flash-attn test for their ring).  Needs >= 2 GPUs: run with
+`gpurun --gpus 2 -- python -m pytest tests/test_gpu_cp.py -m gpu`."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def _worker(rank, world, port):
+    import math
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from long_vita_b200 import cp as CP
+        from long_vita_b200 import ops
+        from long_vita_b200.config import LongVITAConfig
+        from long_vita_b200.hf.modeling import LongVITAForCausalLM
+        from long_vita_b200.synthetic import build_prompt, synthetic_frames
+        from long_vita_b200.weights import synthetic_state_dict
+        from oracle import ops as O
+
+        # ---- kernel level: CPContext.attention over three epochs (both buffer parities) ----
+        hq, hkv, d = 10, 2, 128
+        S = 2 * world * 512
+        ctx = CP.CPContext(dist.group.WORLD, S, hq, hkv, d, dev)
+        own = CP.zigzag_index(S, world, rank)
+        for epoch in range(3):
+            g = torch.Generator().manual_seed(100 + epoch)        # same tensors on every rank
+            qkv = torch.randn(S, (hq + 2 * hkv) * d, generator=g).to(torch.bfloat16)
+            ctx.qkv_buffer().copy_(qkv[own].to(dev))
+            out = ctx.attention()
+            q = qkv[:, : hq * d].view(1, S, hq, d)
+            k = qkv[:, hq * d : (hq + hkv) * d].view(1, S, hkv, d)
+            v = qkv[:, (hq + hkv) * d :].view(1, S, hkv, d)
+            ref, _ = O.attention(q, k, v, causal=True)
+            ref_l = ref[0, own].reshape(own.numel(), hq * d)
+            e = _rel(out, ref_l)
+            e_floor = _rel(ref_l.to(torch.bfloat16), ref_l)
+            assert math.sqrt(max(e * e - e_floor * e_floor, 0.0)) < 2e-3, (rank, epoch, e, e_floor)
+        dist.barrier()
+
+        # ---- whole sharded prefill vs the single-device forward ----
+        cfg = LongVITAConfig.tiny(layers=3, vit_layers=1)
+        w = synthetic_state_dict(cfg, seed=11, dtype=torch.bfloat16, perturb=True)
+        model = LongVITAForCausalLM(cfg, {k_: t.to(dev) for k_, t in w.items()})
+        ids, idx = build_prompt(cfg, 5, n_text=30, pad_multiple=2 * world * 256, seed=3)
+        images = synthetic_frames(cfg, 5, seed=3)
+        single = model(input_ids=ids.to(dev), images=images.to(dev), image_indices=idx.to(dev), num_logits_to_keep=1).logits
+        runner = CP.ContextParallelRunner(model, dist.group.WORLD)
+        for _ in range(2):   # second call re-uses the context (epochs continue)
+            sharded = runner.forward(ids.to(dev), images.to(dev), idx.to(dev))
+            assert _rel(sharded, single) < 1e-2, (rank, _rel(sharded, single))
+            assert int(sharded.float().argmax()) == int(single.float().argmax())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_context_parallel_matches_single_device(lib_built, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    mp.spawn(_worker, args=(world, _free_port()), nprocs=world, join=True)
