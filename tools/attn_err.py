@@ -15,7 +15,7 @@ for (sq, hq, hkv, d, causal) in [(512, 8, 2, 128, True), (1025, 16, 16, 64, Fals
     ref, lse_ref = O.attention(q, k, v, causal=causal)
     out, lse = ops.attention_fwd(q.cuda(), k.cuda(), v.cuda(), causal=causal, return_lse=True)
     et, ef = rel(out, ref), rel(ref.bfloat16(), ref)
-    line = {"P": "bf16" if os.environ.get("LV_ATTN_P_BF16") == "1" else "fp16", "shape": [sq, hq, hkv, d, causal], "e_total": et, "e_floor": ef,
+    line = {"P": "bf16", "shape": [sq, hq, hkv, d, causal], "e_total": et, "e_floor": ef,
             "excess": math.sqrt(max(et * et - ef * ef, 0)), "lse_abs": float((lse.cpu() - lse_ref).abs().max())}
     try:
         import flash_attn
