@@ -182,10 +182,12 @@ def main():
 
     cfg = LongVITAConfig.long_vita_14b()
     cp = max(world, 1)
-    pad = 2 * cp * 128
-    ids, image_indices = build_prompt(cfg, args.frames, args.text, pad_multiple=max(pad, 256))
+    # the SAME prompt at every N: length padded (with text tokens) to a multiple of 2*8*128 so that it
+    # shards zig-zag over 1, 2, 4 or 8 ranks in 128-token units
+    ids, image_indices = build_prompt(cfg, args.frames, args.text, pad_multiple=2048)
     S = ids.shape[1]
-    workload = f"Long-VITA-{'16K' if args.frames == 64 else str(S)} prefill, {args.frames} synthetic frames -> {S} tokens"
+    workload = (f"Long-VITA-{'16K' if args.frames == 64 else str(S)} prefill, {args.frames} synthetic frames "
+                f"({args.frames * 256} visual + {2 * args.frames} delimiter tokens) + text, padded to {S} tokens")
     config = {"workload": workload, "frames": args.frames, "tokens": S, "layers": cfg.num_hidden_layers,
               "parallelism": f"cp{cp}" if cp > 1 else "single",
               "l2": "per-step working set (29.5 GB weights + activations) far exceeds the 126 MB L2"}

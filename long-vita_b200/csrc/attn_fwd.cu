@@ -92,6 +92,64 @@ __device__ __forceinline__ uint4 ld_peer_v4(const void* p) {
   return v;
 }
 
+__device__ __forceinline__ void cp_copier(const CpKParams& cpp, int warp, int lane) {
+      const int cw = blockIdx.x * 2 + (warp - 2);          // copier index
+      const int ncw = gridDim.x * 2;
+      if (cw == 0) {
+        // tell every peer that this rank's K/V rows for this epoch are complete (they were written
+        // by earlier kernels on this stream; the fence orders them before the flag at system scope)
+        __threadfence_system();
+        if (lane < cpp.cp && lane != cpp.rank) st_release_sys(cpp.peer_ready[lane], cpp.epoch1);
+      }
+      uint32_t seen = 1u << cpp.rank;                      // peers whose ready flag has been observed
+      const int vec_per_row = cpp.kv_row_elems / 4;        // 16-byte vectors in one K|V row pair
+      const int vec_per_half = cpp.kv_row_elems / 8;
+      for (int b = cw; b < cpp.nblk_needed; b += ncw) {
+        const int tok0 = b * A_BN;
+        const int chunk = tok0 / cpp.chunk;
+        const int owner = chunk < cpp.cp ? chunk : 2 * cpp.cp - 1 - chunk;
+        const int lrow0 = (chunk < cpp.cp ? 0 : cpp.chunk) + (tok0 - chunk * cpp.chunk);
+        if (!(seen & (1u << owner))) {
+          if (lane == 0)
+            while (ld_acquire_sys(cpp.my_ready + owner) < cpp.epoch1) {
+            }
+          __syncwarp();
+          seen |= 1u << owner;
+        }
+        const __nv_bfloat16* src = cpp.peer_kv[owner] + (long long)lrow0 * cpp.peer_tok_stride;
+        const int total = A_BN * vec_per_row;
+        for (int i0 = 0; i0 < total; i0 += 32 * 4) {
+          uint4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            const int row = i / vec_per_row, col = i - row * vec_per_row;
+            v[u] = ld_peer_v4(src + (long long)row * cpp.peer_tok_stride + col * 8);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            const int row = i / vec_per_row, col = i - row * vec_per_row;
+            __nv_bfloat16* dst = col < vec_per_half
+                                     ? cpp.k_full + (long long)(tok0 + row) * cpp.kv_row_elems + col * 8
+                                     : cpp.v_full + (long long)(tok0 + row) * cpp.kv_row_elems + (col - vec_per_half) * 8;
+            *reinterpret_cast<uint4*>(dst) = v[u];
+          }
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_gpu(cpp.blk_flags + b, cpp.epoch1);
+      }
+      if (cw == 0) {
+        // do not retire before every peer has entered this epoch: a peer's flag for epoch e+1 then
+        // proves it finished reading our epoch e-1 rows (buffer parity reuse, see DESIGN.md)
+        if (lane < cpp.cp && lane != cpp.rank)
+          while (ld_acquire_sys(cpp.my_ready + lane) < cpp.epoch1) {
+          }
+        __syncwarp();
+      }
+}
+
 template <int D>
 struct AttnCfg {
   static constexpr int KV_STAGES = (D == 128) ? 2 : 4;
@@ -499,63 +557,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   } else {
     // =========================== warps 2-3: context-parallel K/V copier ===========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-    if (CP) {
-      const int cw = blockIdx.x * 2 + (warp - 2);          // copier index
-      const int ncw = gridDim.x * 2;
-      if (cw == 0) {
-        // tell every peer that this rank's K/V rows for this epoch are complete (they were written
-        // by earlier kernels on this stream; the fence orders them before the flag at system scope)
-        __threadfence_system();
-        if (lane < cpp.cp && lane != cpp.rank) st_release_sys(cpp.peer_ready[lane], cpp.epoch1);
-      }
-      uint32_t seen = 1u << cpp.rank;                      // peers whose ready flag has been observed
-      const int vec_per_row = cpp.kv_row_elems / 4;        // 16-byte vectors in one K|V row pair
-      const int vec_per_half = cpp.kv_row_elems / 8;
-      for (int b = cw; b < cpp.nblk_needed; b += ncw) {
-        const int tok0 = b * A_BN;
-        const int chunk = tok0 / cpp.chunk;
-        const int owner = chunk < cpp.cp ? chunk : 2 * cpp.cp - 1 - chunk;
-        const int lrow0 = (chunk < cpp.cp ? 0 : cpp.chunk) + (tok0 - chunk * cpp.chunk);
-        if (!(seen & (1u << owner))) {
-          if (lane == 0)
-            while (ld_acquire_sys(cpp.my_ready + owner) < cpp.epoch1) {
-            }
-          __syncwarp();
-          seen |= 1u << owner;
-        }
-        const __nv_bfloat16* src = cpp.peer_kv[owner] + (long long)lrow0 * cpp.peer_tok_stride;
-        const int total = A_BN * vec_per_row;
-        for (int i0 = 0; i0 < total; i0 += 32 * 4) {
-          uint4 v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * 32 + lane;
-            const int row = i / vec_per_row, col = i - row * vec_per_row;
-            v[u] = ld_peer_v4(src + (long long)row * cpp.peer_tok_stride + col * 8);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * 32 + lane;
-            const int row = i / vec_per_row, col = i - row * vec_per_row;
-            __nv_bfloat16* dst = col < vec_per_half
-                                     ? cpp.k_full + (long long)(tok0 + row) * cpp.kv_row_elems + col * 8
-                                     : cpp.v_full + (long long)(tok0 + row) * cpp.kv_row_elems + (col - vec_per_half) * 8;
-            *reinterpret_cast<uint4*>(dst) = v[u];
-          }
-        }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) st_release_gpu(cpp.blk_flags + b, cpp.epoch1);
-      }
-      if (cw == 0) {
-        // do not retire before every peer has entered this epoch: a peer's flag for epoch e+1 then
-        // proves it finished reading our epoch e-1 rows (buffer parity reuse, see DESIGN.md)
-        if (lane < cpp.cp && lane != cpp.rank)
-          while (ld_acquire_sys(cpp.my_ready + lane) < cpp.epoch1) {
-          }
-        __syncwarp();
-      }
-    }
+    if (CP) cp_copier(cpp, warp, lane);
   }
 
   tc_fence_before();
@@ -563,7 +565,414 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int D, bool PF16, bool CP>
+// ================================================================================================
+// Version 2 of the forward kernel: 64-key softmax steps with DOUBLE-BUFFERED S.
+//
+// v1 aliases P over the only S buffer of a query tile, so QK(j+1) cannot be issued before PV(j) and
+// every iteration pays softmax latency + two mbarrier round trips on the tensor pipe's critical
+// path (measured: 55 % tensor-pipe activity, softmax warps idle 47 % of the time waiting for S).
+// Here each query tile owns two 64-column S buffers (TMEM: S0a S0b S1a S1b O0 O1 = 512 columns);
+// the issuer runs one step ahead - QK_t(i+1) is queued before PV_t(i) - so S(i+1) is ready when
+// softmax(i) retires and the chain becomes throughput- (MUFU / tensor) instead of latency-bound.
+// Work per step and query tile: QK 128x64x128, PV 128x128x64.  Causal skipping is also 64-granular.
+// ================================================================================================
+constexpr int A_BH = 64;
+
+struct WorkItem2 {
+  int b, h, kvh;
+  int n[2];           // 64-key steps per query tile
+  long long qpos[2];
+  int row0[2];
+};
+
+__device__ __forceinline__ WorkItem2 decode_item2(const AttnKParams& p, int item) {
+  WorkItem2 w;
+  const int G = p.hq / p.hkv;
+  const int g = item % G;
+  int r = item / G;
+  const int rank = r % p.n_qblk;
+  r /= p.n_qblk;
+  w.kvh = r % p.hkv;
+  w.b = r / p.hkv;
+  w.h = w.kvh * G + g;
+  const int qblk = p.causal ? (p.n_qblk - 1 - rank) : rank;
+  const int n_steps = (p.sk + A_BH - 1) / A_BH;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int row0 = qblk * 256 + t * A_BM;
+    w.row0[t] = row0;
+    const int seg = row0 / p.q_seg_len;
+    w.qpos[t] = (seg == 0 ? p.q_seg_pos0 : p.q_seg_pos1) + (row0 - seg * p.q_seg_len);
+    int n = 0;
+    if (row0 < p.sq) {
+      n = n_steps;
+      if (p.causal) {
+        const long long hi = w.qpos[t] + (A_BM - 1) - p.kv_pos0;
+        if (hi < 0)
+          n = 0;
+        else {
+          const long long lim = hi / A_BH + 1;
+          if (lim < n) n = (int)lim;
+        }
+      }
+    }
+    w.n[t] = n;
+  }
+  return w;
+}
+
+template <int D, bool CP>
+__global__ void __launch_bounds__(A_THREADS, 1)
+    attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                     const AttnKParams p, const CpKParams cpp) {
+  using Cfg = AttnCfg<D>;
+  constexpr int NS = Cfg::KV_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::SMEM_Q;
+  uint8_t* sV = sK + Cfg::SMEM_K;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Cfg::SMEM_V);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* q_empty = bars + 2;       // [2]
+  uint64_t* k_full = bars + 4;        // [NS]
+  uint64_t* k_empty = bars + 4 + NS;
+  uint64_t* v_full = bars + 4 + 2 * NS;
+  uint64_t* v_empty = bars + 4 + 3 * NS;
+  uint64_t* s_full = bars + 4 + 4 * NS;   // [2 tiles][2 buffers]
+  uint64_t* p_full = s_full + 4;          // [2][2]
+  uint64_t* o_done = p_full + 4;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&o_done[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+    }
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S_t[b] at t*128 + b*64; O_t at 256 + t*D
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t item_cnt = 0, kcnt = 0, vcnt = 0;
+      int ready_upto = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+        const WorkItem2 w = decode_item2(p, item);
+        const int ntile = (max(w.n[0], w.n[1]) + 1) / 2;   // 128-row K/V tiles
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&q_empty[t], (item_cnt & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[t], Cfg::TILE_BYTES);
+          for (int bx = 0; bx < Cfg::BOXES; ++bx)
+            tma_load_4d(sQ + t * Cfg::TILE_BYTES + bx * 16384, &tmQ, &q_full[t], bx * 64, w.row0[t], w.h, w.b,
+                        kEvictFirst);
+        }
+        for (int j = 0; j < ntile; ++j) {
+          if (CP && j >= ready_upto) {
+            while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1) {
+            }
+            ready_upto = j + 1;
+            fence_proxy_async_all();
+          }
+          {
+            const int st = kcnt % NS;
+            mbar_wait(&k_empty[st], ((kcnt / NS) & 1) ^ 1);
+            mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
+            for (int bx = 0; bx < Cfg::BOXES; ++bx)
+              tma_load_4d(sK + st * Cfg::TILE_BYTES + bx * 16384, &tmK, &k_full[st], bx * 64, j * A_BN, w.kvh, w.b,
+                          kEvictLast);
+            ++kcnt;
+          }
+          {
+            const int st = vcnt % NS;
+            mbar_wait(&v_empty[st], ((vcnt / NS) & 1) ^ 1);
+            mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
+            for (int bx = 0; bx < Cfg::BOXES; ++bx)
+              tma_load_4d(sV + st * Cfg::TILE_BYTES + bx * 16384, &tmV, &v_full[st], bx * 64, j * A_BN, w.kvh, w.b,
+                          kEvictLast);
+            ++vcnt;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(A_BM, A_BH, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(A_BM, D, 0, 1);
+      uint32_t item_cnt = 0;
+      uint32_t kbase = 0, vbase = 0;            // ring counters of this item's tile 0
+      uint32_t scnt[2][2] = {{0, 0}, {0, 0}};   // completed uses of s_full / p_full [tile][buffer]
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+        const WorkItem2 w = decode_item2(p, item);
+        const int nmax = max(w.n[0], w.n[1]);
+        const int ntile = (nmax + 1) / 2;
+        int k_waited = 0, v_waited = 0;
+        mbar_wait(&q_full[0], item_cnt & 1);
+        mbar_wait(&q_full[1], item_cnt & 1);
+        tc_fence_after();
+
+        auto issue_qk = [&](int t, int i) {
+          const int m = i >> 1;
+          while (k_waited <= m) {
+            const uint32_t c = kbase + k_waited;
+            mbar_wait(&k_full[c % NS], (c / NS) & 1);
+            ++k_waited;
+          }
+          tc_fence_after();
+          const int b = i & 1;
+          const uint32_t qa = smem_u32(sQ + t * Cfg::TILE_BYTES);
+          const uint32_t ka = smem_u32(sK + ((kbase + m) % NS) * Cfg::TILE_BYTES) + (i & 1) * 8192;
+          const uint32_t d_tmem = tmem_base + t * 128 + b * 64;
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
+            umma_ss(d_tmem, make_smem_desc(qa + off, 16, 1024), make_smem_desc(ka + off, 16, 1024), idesc_qk,
+                    kk != 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[t * 2 + b]);
+        };
+        auto issue_pv = [&](int t, int i) {
+          const int m = i >> 1;
+          while (v_waited <= m) {
+            const uint32_t c = vbase + v_waited;
+            mbar_wait(&v_full[c % NS], (c / NS) & 1);
+            ++v_waited;
+          }
+          const int b = i & 1;
+          mbar_wait(&p_full[t * 2 + b], scnt[t][b] & 1);
+          ++scnt[t][b];
+          tc_fence_after();
+          const uint32_t va = smem_u32(sV + ((vbase + m) % NS) * Cfg::TILE_BYTES) + (i & 1) * 8192;
+          const uint32_t a_tmem = tmem_base + t * 128 + b * 64;
+          const uint32_t d_tmem = tmem_base + 256 + t * D;
+#pragma unroll
+          for (int kk = 0; kk < A_BH / 16; ++kk)
+            umma_ts(d_tmem, a_tmem + kk * 8, make_smem_desc(va + kk * 2048, 16384, 1024), idesc_pv,
+                    (i > 0 || kk != 0) ? 1u : 0u);
+          umma_commit(&o_done[t]);
+        };
+
+        for (int t = 0; t < 2; ++t)
+          if (w.n[t] > 0) issue_qk(t, 0);
+        if (nmax == 1) umma_commit(&k_empty[kbase % NS]);
+        for (int i = 0; i < nmax; ++i) {
+          const int s = i + 1;
+          // queue the next step's QK^T of both tiles first (they need no softmax result), so the
+          // tensor pipe has work while this step's probabilities are still being produced
+          if (s < w.n[0]) issue_qk(0, s);
+          if (s < w.n[1]) issue_qk(1, s);
+          if (s < nmax && ((s & 1) == 1 || s == nmax - 1))
+            umma_commit(&k_empty[(kbase + (s >> 1)) % NS]);   // last QK on this K tile has been issued
+          if (i < w.n[0]) issue_pv(0, i);
+          if (i < w.n[1]) issue_pv(1, i);
+          if ((i & 1) == 1 || i == nmax - 1) umma_commit(&v_empty[(vbase + (i >> 1)) % NS]);
+        }
+        kbase += ntile;
+        vbase += ntile;
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================== softmax / epilogue warpgroups ===========================
+    const int t = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int wg_tid = (warp - 4 - 4 * t) * 32 + lane;
+    const uint32_t lane_base = uint32_t(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + t * 128;
+    const uint32_t tO = tmem_base + lane_base + 256 + t * D;
+    uint8_t* stage = sQ + t * Cfg::TILE_BYTES;
+    uint32_t item_cnt = 0;
+    uint32_t scnt[2] = {0, 0};   // uses of s_full[t][b]
+    uint32_t pv_base = 0;        // PV commits on o_done[t] before this item
+
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+      const WorkItem2 w = decode_item2(p, item);
+      const int n = w.n[t];
+      const long long qpos = w.qpos[t] + row;
+      float m_used = 0.f, l = 0.f;
+      for (int i = 0; i < n; ++i) {
+        const int b = i & 1;
+        mbar_wait(&s_full[t * 2 + b], scnt[b] & 1);
+        ++scnt[b];
+        tc_fence_after();
+        uint32_t s[2][32];
+        tmem_ld32(tS + b * 64, s[0]);
+        tmem_ld32(tS + b * 64 + 32, s[1]);
+        tmem_wait_ld();
+
+        const long long kidx0 = (long long)i * A_BH;
+        const bool ragged = kidx0 + A_BH > p.sk;
+        const bool diag = p.causal && (p.kv_pos0 + kidx0 + A_BH - 1 > w.qpos[t]);
+        if (ragged || diag) {
+          long long lim = p.sk - kidx0;
+          if (p.causal) {
+            const long long c = qpos - p.kv_pos0 - kidx0 + 1;
+            if (c < lim) lim = c;
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (c * 32 + k >= lim) s[c][k] = 0xff800000u;
+        }
+
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(s[0][k]), __uint_as_float(s[0][k + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(s[0][k + 2]), __uint_as_float(s[0][k + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(s[1][k]), __uint_as_float(s[1][k + 1]));
+          mx3 = fmax3(mx3, __uint_as_float(s[1][k + 2]), __uint_as_float(s[1][k + 3]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+
+        float alpha = 1.f;
+        bool rescale = false;
+        if (i == 0) {
+          m_used = (mx == -INFINITY) ? 0.f : mx;
+        } else {
+          const bool grow = mx > m_used + 8.f;
+          rescale = __any_sync(0xffffffffu, grow);
+          if (rescale) {
+            const float m_new = fmaxf(m_used, mx);
+            alpha = ex2(m_used - m_new);
+            m_used = m_new;
+            l *= alpha;
+          }
+        }
+
+        const float neg_m = -m_used;
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            const float p0 = ex2(fmaf(__uint_as_float(s[c][k + 0]), p.scale_log2, neg_m));
+            const float p1 = ex2(fmaf(__uint_as_float(s[c][k + 1]), p.scale_log2, neg_m));
+            const float p2 = ex2(fmaf(__uint_as_float(s[c][k + 2]), p.scale_log2, neg_m));
+            const float p3 = ex2(fmaf(__uint_as_float(s[c][k + 3]), p.scale_log2, neg_m));
+            l0 += p0;
+            l1 += p1;
+            l2 += p2;
+            l3 += p3;
+            pk[k / 2] = pack_bf16(p0, p1);
+            pk[k / 2 + 1] = pack_bf16(p2, p3);
+          }
+          tmem_st16(tS + b * 64 + c * 16, pk);
+        }
+        l += (l0 + l1) + (l2 + l3);
+        if (i > 0) {
+          // PV_t(i-1) has normally retired long ago (QK_t(i) was queued before it, a whole softmax step
+          // has passed).  Its phase is consumed here, every step and in order, so this thread can never
+          // fall two phases behind o_done; O_t is rescaled (lazily) only after it.
+          mbar_wait(&o_done[t], (pv_base + i - 1) & 1);
+          if (rescale) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+              tmem_st32(tO + c * 32, o);
+            }
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t * 2 + b]);
+      }
+
+      // ---------------- epilogue ----------------
+      const float inv_l = (n > 0 && l > 0.f) ? 1.f / l : 0.f;
+      if (n > 0) {
+        mbar_wait(&o_done[t], (pv_base + n - 1) & 1);
+        pv_base += n;
+        tc_fence_after();
+      } else {
+        mbar_wait(&q_full[t], item_cnt & 1);
+      }
+#pragma unroll 1
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[32];
+        if (n > 0) {
+          tmem_ld32(tO + c * 32, o);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) o[k] = 0u;
+        }
+        uint8_t* box = stage + (c >> 1) * 16384 + row * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[8 * q + 0]) * inv_l, __uint_as_float(o[8 * q + 1]) * inv_l);
+          v.y = pack_bf16(__uint_as_float(o[8 * q + 2]) * inv_l, __uint_as_float(o[8 * q + 3]) * inv_l);
+          v.z = pack_bf16(__uint_as_float(o[8 * q + 4]) * inv_l, __uint_as_float(o[8 * q + 5]) * inv_l);
+          v.w = pack_bf16(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l);
+          const int chunk = (c & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(box + ((chunk ^ (row & 7)) << 4)) = v;
+        }
+      }
+      tc_fence_before();
+      if (p.lse != nullptr && w.row0[t] + row < p.sq) {
+        const float lse = (n > 0 && l > 0.f) ? (m_used + log2f(l)) * 0.69314718055994530942f : -INFINITY;
+        p.lse[((long long)w.b * p.hq + w.h) * p.sq + w.row0[t] + row] = lse;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + t, 128);
+      if (wg_tid == 0) {
+        if (w.row0[t] < p.sq) {
+          for (int bx = 0; bx < Cfg::BOXES; ++bx) tma_store_4d(&tmO, stage + bx * 16384, bx * 64, w.row0[t], w.h, w.b);
+          tma_store_commit();
+          tma_store_wait_read0();
+        }
+        mbar_arrive(&q_empty[t]);
+      }
+    }
+    if (wg_tid == 0) tma_store_wait_all0();
+  } else {
+    if (CP) cp_copier(cpp, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <int D, bool PF16, bool CP, int VER>
 static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_t s) {
   using Cfg = AttnCfg<D>;
   CUtensorMap tmQ, tmK, tmV, tmO;
@@ -603,7 +1012,11 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
   p.lse = a->lse;
   static bool attr_set = false;
   if (!attr_set) {
-    LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, PF16, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
+    if constexpr (VER == 2) {
+      LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<D, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
+    } else {
+      LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, PF16, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
+    }
     attr_set = true;
   }
   int grid = p.n_items < sm_count() ? p.n_items : sm_count();
@@ -613,7 +1026,10 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
     cpp = *cp;
     grid = sm_count();   // every copier warp takes part, also when there are fewer work items than SMs
   }
-  attn_fwd_kernel<D, PF16, CP><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p, cpp);
+  if constexpr (VER == 2)
+    attn_fwd2_kernel<D, CP><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p, cpp);
+  else
+    attn_fwd_kernel<D, PF16, CP><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p, cpp);
   LV_CHECK_LAUNCH("attn_fwd_kernel");
   return LV_OK;
 }
@@ -621,6 +1037,16 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
 }  // namespace lv
 
 using namespace lv;
+
+// LV_ATTN_VERSION=2 selects the double-buffered-S kernel (experimental: correct, currently slower);
+// default is the single-S-buffer kernel.
+static int attn_version() {
+  static const int v = [] {
+    const char* e = getenv("LV_ATTN_VERSION");
+    return (e != nullptr && e[0] == '2') ? 2 : 1;
+  }();
+  return v;
+}
 
 static int check_attn_params(const lv_attn_params* a) {
   LV_CHECK_ARG(a != nullptr, "lv_attn_fwd: null params");
@@ -632,7 +1058,7 @@ static int check_attn_params(const lv_attn_params* a) {
   LV_CHECK_ARG(a->batch * a->hq * ((a->sq + 255) / 256) < (1ll << 31), "lv_attn_fwd: too many work items");
   LV_CHECK_ARG(a->q_seg_len > 0 && a->q_seg_len <= a->sq, "lv_attn_fwd: q_seg_len=%lld out of range", (long long)a->q_seg_len);
   if (a->q_seg_len < a->sq) {
-    LV_CHECK_ARG(a->q_seg_len % 256 == 0 && a->sq <= 2 * a->q_seg_len, "lv_attn_fwd: segmented queries need q_seg_len %% 256 == 0 and at most two segments");
+    LV_CHECK_ARG(a->q_seg_len % 128 == 0 && a->sq <= 2 * a->q_seg_len, "lv_attn_fwd: segmented queries need q_seg_len %% 128 == 0 (a 128-row query tile never straddles segments) and at most two segments");
   }
   for (int i = 0; i < 3; ++i)
     LV_CHECK_ARG(a->q_strides[i] % 8 == 0 && a->k_strides[i] % 8 == 0 && a->v_strides[i] % 8 == 0 && a->o_strides[i] % 8 == 0,
@@ -646,8 +1072,12 @@ extern "C" int lv_attn_fwd(const lv_attn_params* a, lv_stream_t stream) {
   cudaStream_t s = (cudaStream_t)stream;
   // P is bf16 like V: tcgen05 kind::f16 faults on an fp16 A operand against a bf16 B operand
   // (measured on B200), so the fp16-P instantiation is never launched.
-  if (a->d == 128) return launch_attn<128, false, false>(a, nullptr, s);
-  return launch_attn<64, false, false>(a, nullptr, s);
+  if (attn_version() == 2) {
+    if (a->d == 128) return launch_attn<128, false, false, 2>(a, nullptr, s);
+    return launch_attn<64, false, false, 2>(a, nullptr, s);
+  }
+  if (a->d == 128) return launch_attn<128, false, false, 1>(a, nullptr, s);
+  return launch_attn<64, false, false, 1>(a, nullptr, s);
 }
 
 extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv_stream_t stream) {
@@ -660,7 +1090,7 @@ extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv
   const int64_t S = c->seq_total;
   LV_CHECK_ARG(S % (2 * c->cp) == 0, "lv_attn_cp_fwd: seq_total %lld not divisible by 2*cp", (long long)S);
   const int64_t chunk = S / (2 * c->cp);
-  LV_CHECK_ARG(chunk % 256 == 0, "lv_attn_cp_fwd: chunk %lld must be a multiple of 256 tokens", (long long)chunk);
+  LV_CHECK_ARG(chunk % 128 == 0, "lv_attn_cp_fwd: chunk %lld must be a multiple of 128 tokens", (long long)chunk);
   LV_CHECK_ARG(a->sq == 2 * chunk && a->sk == S && a->q_seg_len == chunk && a->kv_pos0 == 0,
                "lv_attn_cp_fwd: expects sq = 2*chunk local queries against the S-row staging buffers");
   LV_CHECK_ARG(a->q_seg_pos[0] == c->rank * chunk && a->q_seg_pos[1] == (2 * c->cp - 1 - c->rank) * chunk,
@@ -686,7 +1116,8 @@ extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv
   k.k_full = reinterpret_cast<__nv_bfloat16*>(c->k_full);
   k.v_full = reinterpret_cast<__nv_bfloat16*>(c->v_full);
   k.blk_flags = reinterpret_cast<uint32_t*>(c->blk_flags);
-  return launch_attn<128, false, true>(a, &k, (cudaStream_t)stream);
+  if (attn_version() == 2) return launch_attn<128, false, true, 2>(a, &k, (cudaStream_t)stream);
+  return launch_attn<128, false, true, 1>(a, &k, (cudaStream_t)stream);
 }
 
 // Peer-mappable ("symmetric") allocations for the context-parallel K/V exchange: plain cudaMalloc

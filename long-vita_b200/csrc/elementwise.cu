@@ -69,12 +69,12 @@ __device__ __forceinline__ float row_reduce_sum(float v, float* smem, int row_in
 // RMSNorm (+ fused residual add)
 // ---------------------------------------------------------------------------------------------
 template <int TPR, int VPT>
-__global__ void __launch_bounds__(256) rmsnorm_kernel(const __nv_bfloat16* __restrict__ x,
-                                                      const __nv_bfloat16* __restrict__ res,
-                                                      const __nv_bfloat16* __restrict__ w,
-                                                      __nv_bfloat16* __restrict__ y,
-                                                      __nv_bfloat16* __restrict__ sum_out, int64_t rows, int cols,
-                                                      float eps) {
+__global__ void __launch_bounds__(256, 3) rmsnorm_kernel(const __nv_bfloat16* __restrict__ x,
+                                                         const __nv_bfloat16* __restrict__ res,
+                                                         const __nv_bfloat16* __restrict__ w,
+                                                         __nv_bfloat16* __restrict__ y,
+                                                         __nv_bfloat16* __restrict__ sum_out, int64_t rows, int cols,
+                                                         float eps) {
   constexpr int RPC = 256 / TPR;
   __shared__ float red[RPC * (TPR > 32 ? TPR / 32 : 1)];
   const int row_in_cta = threadIdx.x / TPR;
@@ -82,25 +82,36 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const __nv_bfloat16* __res
   const int64_t row = (int64_t)blockIdx.x * RPC + row_in_cta;
   const bool row_ok = row < rows;
   const int nvec = cols / 8;
-  float v[VPT][8];
+  // the row stays in registers as packed bf16 (4 registers per 8 elements): all loads are issued
+  // up front, occupancy stays high, and the second pass needs no re-read
+  Vec8 raw[VPT];
+  Vec8 rr[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = t + i * TPR;
+    if (row_ok && c < nvec) {
+      raw[i] = ldg_stream(x + row * cols + c * 8);
+      if (res != nullptr) rr[i] = ldg_stream(res + row * cols + c * 8);
+    }
+  }
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int c = t + i * TPR;
     if (row_ok && c < nvec) {
-      unpack(ldg_stream(x + row * cols + c * 8), v[i]);
+      float v[8];
+      unpack(raw[i], v);
       if (res != nullptr) {
         float r[8];
-        unpack(ldg_stream(res + row * cols + c * 8), r);
+        unpack(rr[i], r);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] = bf16r(v[i][j] + r[j]);
-        if (sum_out != nullptr) stg_vec(sum_out + row * cols + c * 8, pack(v[i]));
+        for (int j = 0; j < 8; ++j) v[j] = v[j] + r[j];
+        raw[i] = pack(v);          // bf16(x + residual): the new residual stream
+        unpack(raw[i], v);
+        if (sum_out != nullptr) stg_vec(sum_out + row * cols + c * 8, raw[i]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
     }
   }
   ss = row_reduce_sum<TPR>(ss, red, row_in_cta, t);
@@ -109,10 +120,11 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const __nv_bfloat16* __res
   for (int i = 0; i < VPT; ++i) {
     const int c = t + i * TPR;
     if (row_ok && c < nvec) {
-      float wv[8], o[8];
+      float v[8], wv[8], o[8];
+      unpack(raw[i], v);
       unpack(ldg_vec(w + c * 8), wv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = bf16r(v[i][j] * rstd) * wv[j];
+      for (int j = 0; j < 8; ++j) o[j] = bf16r(v[j] * rstd) * wv[j];
       stg_vec(y + row * cols + c * 8, pack(o));
     }
   }
@@ -206,36 +218,49 @@ __global__ void rope_table_kernel(const int64_t* __restrict__ pos, const float* 
   sin_o[i * dim + half + j] = s;
 }
 
-// one thread: 8 elements of the first half and the matching 8 of the second half
+// one thread: 8 elements of the first half and the matching 8 of the second half, for HPT heads of
+// one token (cos / sin are loaded once and reused across those heads)
+template <int HPT>
 __global__ void __launch_bounds__(256) rope_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                    const __nv_bfloat16* __restrict__ cos_t,
                                                    const __nv_bfloat16* __restrict__ sin_t, int64_t n_tok, int heads,
                                                    int dim, int64_t xts, int64_t xhs, int64_t ots, int64_t ohs) {
   const int vph = dim / 16;  // vectors (of 8) per half
+  const int hgroups = heads / HPT;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = n_tok * heads * vph;
+  const int64_t total = n_tok * hgroups * vph;
   if (idx >= total) return;
   const int vi = (int)(idx % vph);
-  const int h = (int)((idx / vph) % heads);
-  const int64_t tok = idx / ((int64_t)vph * heads);
+  const int hg = (int)((idx / vph) % hgroups);
+  const int64_t tok = idx / ((int64_t)vph * hgroups);
   const int half = dim / 2;
-  const __nv_bfloat16* xp = x + tok * xts + (int64_t)h * xhs + vi * 8;
-  float x1[8], x2[8], c1[8], c2[8], s1[8], s2[8], o1[8], o2[8];
-  unpack(ldg_vec(xp), x1);
-  unpack(ldg_vec(xp + half), x2);
+  float c1[8], c2[8], s1[8], s2[8];
   unpack(ldg_vec(cos_t + tok * dim + vi * 8), c1);
   unpack(ldg_vec(cos_t + tok * dim + half + vi * 8), c2);
   unpack(ldg_vec(sin_t + tok * dim + vi * 8), s1);
   unpack(ldg_vec(sin_t + tok * dim + half + vi * 8), s2);
+  Vec8 a[HPT], b[HPT];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    // (t * cos) + (rotate_half(t) * sin), each product and the sum rounded to bf16
-    o1[j] = bf16r(x1[j] * c1[j]) + bf16r(-x2[j] * s1[j]);
-    o2[j] = bf16r(x2[j] * c2[j]) + bf16r(x1[j] * s2[j]);
+  for (int h = 0; h < HPT; ++h) {
+    const __nv_bfloat16* xp = x + tok * xts + (int64_t)(hg * HPT + h) * xhs + vi * 8;
+    a[h] = ldg_vec(xp);
+    b[h] = ldg_vec(xp + half);
   }
-  __nv_bfloat16* op = out + tok * ots + (int64_t)h * ohs + vi * 8;
-  stg_vec(op, pack(o1));
-  stg_vec(op + half, pack(o2));
+#pragma unroll
+  for (int h = 0; h < HPT; ++h) {
+    float x1[8], x2[8], o1[8], o2[8];
+    unpack(a[h], x1);
+    unpack(b[h], x2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // (t * cos) + (rotate_half(t) * sin), each product and the sum rounded to bf16
+      o1[j] = bf16r(x1[j] * c1[j]) + bf16r(-x2[j] * s1[j]);
+      o2[j] = bf16r(x2[j] * c2[j]) + bf16r(x1[j] * s2[j]);
+    }
+    __nv_bfloat16* op = out + tok * ots + (int64_t)(hg * HPT + h) * ohs + vi * 8;
+    stg_vec(op, pack(o1));
+    stg_vec(op + half, pack(o2));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -251,7 +276,7 @@ __global__ void __launch_bounds__(256) swiglu_kernel(const __nv_bfloat16* __rest
   unpack(ldg_stream(gu + r * 2 * inter + c * 8), g);
   unpack(ldg_stream(gu + r * 2 * inter + inter + c * 8), u);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = bf16r(g[j] / (1.f + expf(-g[j]))) * u[j];
+  for (int j = 0; j < 8; ++j) o[j] = bf16r(__fdividef(g[j], 1.f + __expf(-g[j]))) * u[j];
   stg_vec(out + r * inter + c * 8, pack(o));
 }
 
@@ -434,10 +459,19 @@ int lv_rope(const void* x, void* out, const void* cos_t, const void* sin_t, int6
                "lv_rope: strides must be multiples of 8 elements");
   LV_CHECK_ARG(aligned16(x) && aligned16(out) && aligned16(cos_t) && aligned16(sin_t), "lv_rope: pointers must be 16-byte aligned");
   if (n_tok == 0 || heads == 0) return LV_OK;
-  const int64_t total = n_tok * heads * (dim / 16);
-  rope_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(BF(x), BFM(out), BF(cos_t), BF(sin_t), n_tok,
-                                                                           (int)heads, (int)dim, x_tok_stride,
-                                                                           x_head_stride, o_tok_stride, o_head_stride);
+#define LAUNCH_ROPE(HPT)                                                                                         \
+  rope_kernel<HPT><<<(unsigned)cdiv(n_tok * (heads / HPT) * (dim / 16), 256), 256, 0, (cudaStream_t)stream>>>(        \
+      BF(x), BFM(out), BF(cos_t), BF(sin_t), n_tok, (int)heads, (int)dim, x_tok_stride, x_head_stride, o_tok_stride, \
+      o_head_stride)
+  if (heads % 8 == 0)
+    LAUNCH_ROPE(8);
+  else if (heads % 5 == 0)
+    LAUNCH_ROPE(5);
+  else if (heads % 2 == 0)
+    LAUNCH_ROPE(2);
+  else
+    LAUNCH_ROPE(1);
+#undef LAUNCH_ROPE
   LV_CHECK_LAUNCH("rope_kernel");
   return LV_OK;
 }

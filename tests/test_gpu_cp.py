@@ -42,7 +42,7 @@ def _worker(rank, world, port):
 
         # ---- kernel level: CPContext.attention over three epochs (both buffer parities) ----
         hq, hkv, d = 10, 2, 128
-        S = 2 * world * 512
+        S = 2 * world * 384          # chunk = 384: a multiple of 128 but not of 256
         ctx = CP.CPContext(dist.group.WORLD, S, hq, hkv, d, dev)
         own = CP.zigzag_index(S, world, rank)
         for epoch in range(3):
@@ -64,7 +64,7 @@ def _worker(rank, world, port):
         cfg = LongVITAConfig.tiny(layers=3, vit_layers=1)
         w = synthetic_state_dict(cfg, seed=11, dtype=torch.bfloat16, perturb=True)
         model = LongVITAForCausalLM(cfg, {k_: t.to(dev) for k_, t in w.items()})
-        ids, idx = build_prompt(cfg, 5, n_text=30, pad_multiple=2 * world * 256, seed=3)
+        ids, idx = build_prompt(cfg, 5, n_text=30, pad_multiple=2 * world * 128, seed=3)
         images = synthetic_frames(cfg, 5, seed=3)
         single = model(input_ids=ids.to(dev), images=images.to(dev), image_indices=idx.to(dev), num_logits_to_keep=1).logits
         runner = CP.ContextParallelRunner(model, dist.group.WORLD)
