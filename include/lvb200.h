@@ -81,6 +81,32 @@ typedef struct lv_attn_params {
 int lv_attn_fwd(const lv_attn_params* p, lv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Attention (backward): dQ, dK, dV of lv_attn_fwd.
+ *
+ * Replaces flash-attn 2's backward, which the reference reaches through autograd of
+ * flash_attn_func / _flash_attention_forward (dot_product_attention.py:318-326, 374-390) during
+ * pretrain_long_vita.py.  `fwd` repeats the forward call's arguments with `out` and `lse` holding the
+ * forward results (lse is required).  d_out has the layout of out; dq / dk / dv have the shapes of
+ * q / k / v (GQA: dk, dv are summed over the query heads of each group).  delta_ws is caller
+ * workspace of batch*hq*sq floats.  Deterministic (no atomics): two tensor-core passes, one for
+ * dK/dV and one for dQ.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lv_attn_bwd_params {
+  lv_attn_params fwd;
+  const void* d_out;      /* bf16 [b, sq, hq, d]  */
+  void* dq;               /* bf16 [b, sq, hq, d]  */
+  void* dk;               /* bf16 [b, sk, hkv, d] */
+  void* dv;               /* bf16 [b, sk, hkv, d] */
+  int64_t do_strides[3];  /* batch, seq, head */
+  int64_t dq_strides[3];
+  int64_t dk_strides[3];
+  int64_t dv_strides[3];
+  float* delta_ws;        /* float [b, hq, sq] */
+} lv_attn_bwd_params;
+
+int lv_attn_bwd(const lv_attn_bwd_params* p, lv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Context-parallel attention (forward): zig-zag sequence sharding with the K/V exchange inside the
  * attention kernel.
  *

@@ -34,6 +34,16 @@ class AttnParams(C.Structure):
     ]
 
 
+class AttnBwdParams(C.Structure):
+    """Mirror of `lv_attn_bwd_params` (include/lvb200.h)."""
+
+    _fields_ = [
+        ("fwd", AttnParams), ("d_out", c_ptr), ("dq", c_ptr), ("dk", c_ptr), ("dv", c_ptr),
+        ("do_strides", c_i64 * 3), ("dq_strides", c_i64 * 3), ("dk_strides", c_i64 * 3), ("dv_strides", c_i64 * 3),
+        ("delta_ws", c_ptr),
+    ]
+
+
 class CpParams(C.Structure):
     """Mirror of `lv_cp_params` (include/lvb200.h)."""
 
@@ -50,6 +60,7 @@ SIGNATURES = {
     "lv_last_error": (C.c_char_p, []),
     "lv_launch_count": (c_i64, []),
     "lv_attn_fwd": (c_i32, [C.POINTER(AttnParams), c_ptr]),
+    "lv_attn_bwd": (c_i32, [C.POINTER(AttnBwdParams), c_ptr]),
     "lv_attn_cp_fwd": (c_i32, [C.POINTER(AttnParams), C.POINTER(CpParams), c_ptr]),
     "lv_ipc_alloc": (c_i32, [c_i64, C.POINTER(c_ptr)]),
     "lv_ipc_free": (c_i32, [c_ptr]),

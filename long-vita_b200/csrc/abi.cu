@@ -31,6 +31,37 @@ int sm_count() {
   return cached[dev];
 }
 
+int bind_device(const void* ptr) {
+  if (ptr == nullptr) return LV_OK;
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaPointerGetAttributes failed: %s", cudaGetErrorString(e));
+    return LV_ECUDA;
+  }
+  if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) {
+    set_error("pointer %p is not device memory", ptr);
+    return LV_EINVAL;
+  }
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != attr.device) {
+    e = cudaSetDevice(attr.device);
+    if (e != cudaSuccess) {
+      set_error("cudaSetDevice(%d) failed: %s", attr.device, cudaGetErrorString(e));
+      return LV_ECUDA;
+    }
+  }
+  // cudaSetDevice is lazy about the driver context on some paths; a no-op runtime call binds it
+  // (once per host thread and device)
+  static thread_local int bound = -1;
+  if (bound != attr.device) {
+    if (cudaFree(nullptr) != cudaSuccess) cudaGetLastError();
+    bound = attr.device;
+  }
+  return LV_OK;
+}
+
 typedef CUresult (*encode_fn_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

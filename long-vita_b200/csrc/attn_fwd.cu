@@ -1069,6 +1069,7 @@ static int check_attn_params(const lv_attn_params* a) {
 extern "C" int lv_attn_fwd(const lv_attn_params* a, lv_stream_t stream) {
   int rc = check_attn_params(a);
   if (rc) return rc;
+  LV_BIND_DEVICE(a->q);
   cudaStream_t s = (cudaStream_t)stream;
   // P is bf16 like V: tcgen05 kind::f16 faults on an fp16 A operand against a bf16 B operand
   // (measured on B200), so the fp16-P instantiation is never launched.
@@ -1083,6 +1084,7 @@ extern "C" int lv_attn_fwd(const lv_attn_params* a, lv_stream_t stream) {
 extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv_stream_t stream) {
   int rc = check_attn_params(a);
   if (rc) return rc;
+  LV_BIND_DEVICE(a->q);
   LV_CHECK_ARG(c != nullptr, "lv_attn_cp_fwd: null cp params");
   LV_CHECK_ARG(c->cp >= 2 && c->cp <= 8 && c->rank >= 0 && c->rank < c->cp, "lv_attn_cp_fwd: bad rank %d / cp %d", c->rank, c->cp);
   LV_CHECK_ARG(a->batch == 1 && a->causal, "lv_attn_cp_fwd: batch 1, causal only");

@@ -15,12 +15,21 @@ namespace lv {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int sm_count();
+// Make the device that owns `ptr` current on the calling thread (autograd runs backward on its own
+// threads, which may have no current CUDA context yet).  Returns LV_OK or LV_ECUDA.
+int bind_device(const void* ptr);
 
 // Encode a bf16 tiled tensor map.  dims/strides innermost-first; strides in BYTES for dims 1..rank-1
 // (dim 0 is contiguous).  box = tile extents, innermost-first.  swizzle128: 128-byte swizzle
 // (box[0] * 2 bytes must be <= 128), otherwise no swizzle.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
+#define LV_BIND_DEVICE(ptr)                \
+  do {                                     \
+    int _r = lv::bind_device(ptr);         \
+    if (_r != LV_OK) return _r;            \
+  } while (0)
 
 #define LV_CHECK_ARG(cond, ...)   \
   do {                            \

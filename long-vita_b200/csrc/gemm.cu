@@ -318,6 +318,7 @@ int lv_gemm_bias_act(const void* A, const void* W, const void* bias, void* C, in
                "lv_gemm_bias_act: leading dimensions must be >= the row length and multiples of 8");
   LV_CHECK_ARG(act >= 0 && act <= 2, "lv_gemm_bias_act: unknown activation %d", act);
   if (M == 0) return LV_OK;
+  LV_BIND_DEVICE(A);
   return launch_gemm(A, W, bias, C, M, N, K, lda, ldw, ldc, act, (cudaStream_t)stream);
 }
 
@@ -332,6 +333,7 @@ int lv_patch_embed(const void* images, const void* W, const void* bias, const vo
   LV_CHECK_ARG(images && W && cls && pos && out && ws, "lv_patch_embed: null pointer");
   LV_CHECK_ARG(img > 0 && ps > 0 && img % ps == 0 && C % 8 == 0, "lv_patch_embed: bad geometry img=%lld ps=%lld C=%lld", (long long)img, (long long)ps, (long long)C);
   if (n == 0) return LV_OK;
+  LV_BIND_DEVICE(images);
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t P = (img / ps) * (img / ps);
   const int64_t kpad = ((3 * ps * ps + 63) / 64) * 64;

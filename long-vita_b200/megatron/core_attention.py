@@ -45,6 +45,11 @@ def _attention_sbhd(query, key, value, causal: bool, scale: float, cp_ctx=None):
             raise AssertionError("context-parallel attention supports micro-batch 1 (the reference's long-context setting)")
         out = cp_ctx.attention_separate(query[:, 0], key[:, 0], value[:, 0], scale=scale)   # [sq, np*hn]
         return out.view(sq, 1, np_ * hn)
+    if torch.is_grad_enabled() and (query.requires_grad or key.requires_grad or value.requires_grad):
+        # training: differentiable path (lv_attn_bwd through torch.autograd.Function)
+        out = ops.attention(query.permute(1, 0, 2, 3), key.permute(1, 0, 2, 3), value.permute(1, 0, 2, 3),
+                            causal=causal, scale=scale)                       # [b, sq, np, hn]
+        return out.permute(1, 0, 2, 3).reshape(sq, b, np_ * hn)
     out = ops.attention_fwd(query, key, value, causal=causal, scale=scale, layout="sbhd")
     return out.reshape(sq, b, np_ * hn)
 

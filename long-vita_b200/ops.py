@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import AttnParams
+from ._lib import AttnBwdParams, AttnParams
 
 
 def _stream() -> int:
@@ -146,6 +146,69 @@ def attention_fwd(
             fl = 4.0 * b * hq * d * sq * sk  # upper bound for masked / segmented calls
         _TIMER.stop("attn_fwd", fl, ev0)
     return (out, lse) if return_lse else out
+
+
+def _fill_attn_params(p, qv, kv_, vv, ov, lse, scale, causal, q_seg_len, q_seg_pos, kv_pos0):
+    b, sq, hq, d = qv.shape
+    _, sk, hkv, _ = kv_.shape
+    p.q, p.k, p.v, p.out = qv.data_ptr(), kv_.data_ptr(), vv.data_ptr(), ov.data_ptr()
+    p.lse = _ptr(lse)
+    p.batch, p.sq, p.sk, p.hq, p.hkv, p.d = b, sq, sk, hq, hkv, d
+    for name, t in (("q_strides", qv), ("k_strides", kv_), ("v_strides", vv), ("o_strides", ov)):
+        arr = getattr(p, name)
+        arr[0], arr[1], arr[2] = t.stride(0), t.stride(1), t.stride(2)
+    p.scale = float(scale if scale is not None else 1.0 / math.sqrt(d))
+    p.causal = 1 if causal else 0
+    p.q_seg_len = int(q_seg_len if q_seg_len is not None else sq)
+    if q_seg_pos is None:
+        q_seg_pos = (sk - sq, 0)
+    p.q_seg_pos[0], p.q_seg_pos[1] = int(q_seg_pos[0]), int(q_seg_pos[1])
+    p.kv_pos0 = int(kv_pos0)
+
+
+def attention_bwd(d_out, q, k, v, out, lse, *, causal: bool, scale: Optional[float] = None, q_seg_len=None,
+                  q_seg_pos=None, kv_pos0: int = 0):
+    """Gradients of attention_fwd (layout "bshd").  `out` / `lse` are the forward results.
+    Returns (dq, dk, dv) with the shapes of q, k, v."""
+    _need_cuda_bf16(d_out, q, k, v, out)
+    _need_cuda(lse, torch.float32)
+
+    def fix(t):
+        return t if (t.stride(3) == 1 and all(s % 8 == 0 for s in t.stride()[:3])) else t.contiguous()
+
+    q, k, v, out, d_out = fix(q), fix(k), fix(v), fix(out), fix(d_out)
+    dq, dk, dv = torch.empty_like(q, memory_format=torch.contiguous_format), \
+        torch.empty_like(k, memory_format=torch.contiguous_format), torch.empty_like(v, memory_format=torch.contiguous_format)
+    b, sq, hq, _ = q.shape
+    delta = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)
+    p = AttnBwdParams()
+    _fill_attn_params(p.fwd, q, k, v, out, lse.contiguous(), scale, causal, q_seg_len, q_seg_pos, kv_pos0)
+    p.d_out, p.dq, p.dk, p.dv, p.delta_ws = d_out.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), delta.data_ptr()
+    for name, t in (("do_strides", d_out), ("dq_strides", dq), ("dk_strides", dk), ("dv_strides", dv)):
+        arr = getattr(p, name)
+        arr[0], arr[1], arr[2] = t.stride(0), t.stride(1), t.stride(2)
+    _lib.check(_lib.lib().lv_attn_bwd(C.byref(p), _stream()), "lv_attn_bwd")
+    return dq, dk, dv
+
+
+class _AttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, causal, scale):
+        out, lse = attention_fwd(q, k, v, causal=causal, scale=scale, return_lse=True)
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.causal, ctx.scale = causal, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, k, v, out, lse = ctx.saved_tensors
+        dq, dk, dv = attention_bwd(d_out.contiguous(), q, k, v, out, lse, causal=ctx.causal, scale=ctx.scale)
+        return dq, dk, dv, None, None
+
+
+def attention(q, k, v, *, causal: bool, scale: Optional[float] = None):
+    """Differentiable fused attention, "bshd" layout (the autograd twin of flash_attn_func)."""
+    return _AttentionFn.apply(q, k, v, causal, scale)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -78,6 +78,29 @@ def attention(
     return out.permute(0, 2, 1, 3).contiguous(), lse
 
 
+def attention_grads(q, k, v, d_out, *, causal: bool, scale: Optional[float] = None, q_pos=None, kv_pos=None):
+    """dq, dk, dv of `attention` by fp32 autograd over the same definition (the reference gets them
+    from flash-attn 2's backward through autograd; no separate formula exists in the reference)."""
+    qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    b, sq, hq, d = qf.shape
+    sk, hkv = kf.shape[1], kf.shape[2]
+    g = hq // hkv
+    scale = 1.0 / math.sqrt(d) if scale is None else scale
+    if q_pos is None:
+        q_pos = torch.arange(sq, dtype=torch.int64) + (sk - sq)
+    if kv_pos is None:
+        kv_pos = torch.arange(sk, dtype=torch.int64)
+    kk = kf.repeat_interleave(g, dim=2)
+    vv = vf.repeat_interleave(g, dim=2)
+    s = torch.einsum("bqhd,bkhd->bhqk", qf, kk) * scale
+    if causal:
+        s = s.masked_fill(kv_pos[None, :] > q_pos[:, None], float("-inf"))
+    p = torch.nan_to_num(torch.softmax(s, dim=-1), nan=0.0)
+    out = torch.einsum("bhqk,bkhd->bqhd", p, vv)
+    out.backward(d_out.float())
+    return qf.grad, kf.grad, vf.grad
+
+
 def zigzag_positions(seq_len: int, cp: int, rank: int) -> torch.Tensor:
     """Global positions owned by `rank`: chunks {r, 2cp-1-r} of 2cp equal chunks
     (long_vita_megatron/training/utils.py:329-341, generation.py:517-539)."""
