@@ -227,8 +227,10 @@ int lv_row_scatter_zero(const void* x, const int64_t* idx, void* out, int64_t n_
  * fp32 accumulate, bf16 out.  Replaces torch.matmul / te.Linear at layers.py:270,409, the ViT
  * qkv/proj/fc1/fc2 (modeling_intern_vit.py:131,141,190-191) and the projector
  * (resampler_projector.py:19-23).  K must be a multiple of 8 (16-byte rows).
- * act: 0 none, 1 exact GELU, 2 tanh GELU, 3 SwiGLU over interleaved column pairs is NOT used;
- * SwiGLU is a separate pass (lv_swiglu).  lda / ldw / ldc are row strides in elements.
+ * act: 0 none, 1 exact GELU, 2 tanh GELU, 3 fused SwiGLU: W rows are interleaved (gate_i, up_i), C is
+ * [M, N/2] with C[:, i] = bf16(silu(bf16 gate_i)) * bf16(up_i) - the rounding sequence of act 0 followed
+ * by lv_swiglu - so the [M, 2*inter] intermediate never reaches HBM (bias must be NULL).
+ * lda / ldw / ldc are row strides in elements.
  * ------------------------------------------------------------------------------------------ */
 int lv_gemm_bias_act(const void* A, const void* W, const void* bias, void* C, int64_t M, int64_t N,
                      int64_t K, int64_t lda, int64_t ldw, int64_t ldc, int32_t act, lv_stream_t stream);

@@ -275,7 +275,7 @@ class ContextParallelRunner:
             att = ctx.attention()
             o = ops.linear(att, layer.wo)
             h, x = ops.rmsnorm(o, layer.ln2, cfg.rms_norm_eps, residual=x)
-            a = ops.swiglu(ops.linear(h, layer.w_gate_up))
+            a = ops.linear(h, layer.w_gate_up, act="swiglu")
             delta = ops.linear(a, layer.w_down)
         h, _ = ops.rmsnorm(delta, m.norm_w, cfg.rms_norm_eps, residual=x)
         # logit mask: each rank projects its own last row; the globally-last token lives on rank 0

@@ -44,6 +44,7 @@ struct AttnKParams {
   long long q_seg_pos0, q_seg_pos1, kv_pos0;
   int n_qblk;      // ceil(sq / 256)
   int n_items;     // batch * hq * n_qblk
+  int block_major; // 1: order work items (q-block, kv-head, head) - global longest-first; 0: (kv-head, q-block, head)
   float* lse;
 };
 
@@ -163,6 +164,35 @@ struct AttnCfg {
   static constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 256 + D;
 };
 
+// Static work assignment: the item list is sorted longest-first; CTAs sweep it boustrophedon (round r
+// forwards, round r+1 backwards) so every CTA receives a near-equal share of causal work without a
+// global atomic.  All warp roles of a CTA evaluate the same sequence.
+__device__ __forceinline__ int sched_item(int round, int n_items) {
+  const int base = round * (int)gridDim.x;
+  if (base >= n_items) return -1;
+  const int item = base + ((round & 1) ? ((int)gridDim.x - 1 - (int)blockIdx.x) : (int)blockIdx.x);
+  return item < n_items ? item : -1;
+}
+
+// (b, kv head, q-block rank, head-in-group) of a work item.  Head-major order keeps one kv head's K/V
+// hot in L2 when all heads do not fit; block-major order is globally longest-first (better balance).
+__device__ __forceinline__ void split_item(const AttnKParams& p, int item, int& b, int& kvh, int& rank, int& g) {
+  const int G = p.hq / p.hkv;
+  g = item % G;
+  int r = item / G;
+  if (p.block_major) {
+    kvh = r % p.hkv;
+    r /= p.hkv;
+    rank = r % p.n_qblk;
+    b = r / p.n_qblk;
+  } else {
+    rank = r % p.n_qblk;
+    r /= p.n_qblk;
+    kvh = r % p.hkv;
+    b = r / p.hkv;
+  }
+}
+
 struct WorkItem {
   int b, h, kvh, qblk;
   int n[2];          // kv tiles each query tile attends to (0: nothing to do)
@@ -173,12 +203,8 @@ struct WorkItem {
 __device__ __forceinline__ WorkItem decode_item(const AttnKParams& p, int item) {
   WorkItem w;
   const int G = p.hq / p.hkv;
-  const int g = item % G;
-  int r = item / G;
-  const int rank = r % p.n_qblk;
-  r /= p.n_qblk;
-  w.kvh = r % p.hkv;
-  w.b = r / p.hkv;
+  int g, rank;
+  split_item(p, item, w.b, w.kvh, rank, g);
   w.h = w.kvh * G + g;
   w.qblk = p.causal ? (p.n_qblk - 1 - rank) : rank;   // heaviest causal blocks first
   const int n_kv_tiles = (p.sk + A_BN - 1) / A_BN;
@@ -206,7 +232,9 @@ __device__ __forceinline__ WorkItem decode_item(const AttnKParams& p, int item) 
   return w;
 }
 
-template <int D, bool PF16, bool CP>
+// QH (quarter hand-off): the softmax warps publish P in four 32-key quarters and the issuer starts the
+// P.V k-steps of a quarter as soon as it lands, so the PV MMA overlaps the exp phase of the same tile.
+template <int D, bool QH, bool CP>
 __global__ void __launch_bounds__(A_THREADS, 1)
     attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -228,7 +256,8 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   uint64_t* s_full = bars + 4 + 4 * NS;   // [2]
   uint64_t* p_full = s_full + 2;          // [2]
   uint64_t* o_full = p_full + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* p_q = o_full + 2;             // [2 tiles][4 quarters]  (QH only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_q + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -245,6 +274,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&p_q[i], 4);
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -268,7 +298,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     if (lane == 0) {
       uint32_t item_cnt = 0, kcnt = 0, vcnt = 0;
       int ready_upto = 0;   // CP: key blocks [0, ready_upto) are known to be staged
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+      for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
         const WorkItem w = decode_item(p, item);
         const int nmax = max(w.n[0], w.n[1]);
         for (int t = 0; t < 2; ++t) {
@@ -311,9 +341,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(A_BM, A_BN, 0, 0);
-      // P is the A operand: bf16, or fp16 (format code 0) when PF16 - kind::f16 takes the A and B
-      // element formats independently, and fp16's 11-bit mantissa removes most of the P rounding error
-      constexpr uint32_t idesc_pv = make_idesc_bf16(A_BM, D, 0, 1) & ~(PF16 ? (7u << 7) : 0u);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(A_BM, D, 0, 1);
       const uint32_t tS[2] = {tmem_base + Cfg::TM_S0, tmem_base + Cfg::TM_S1};
       const uint32_t tO[2] = {tmem_base + Cfg::TM_O0, tmem_base + Cfg::TM_O1};
       uint32_t item_cnt = 0, kcnt = 0, vcnt_wait = 0, vcnt_rel = 0;
@@ -333,6 +361,10 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         const uint32_t va = smem_u32(sV + vst * Cfg::TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < A_BN / 16; ++kk) {
+          if (QH && (kk & 1) == 0) {
+            mbar_wait(&p_q[t * 4 + kk / 2], (pcnt[t] - 1) & 1);   // pcnt[t] was advanced by the caller
+            tc_fence_after();
+          }
           // A: P_t rows in TMEM, 16 bf16 (= 8 columns) per k-step.  B: V tile, MN-major: 16 key rows
           // (2 KB) per k-step, the second 64 head-dim columns live one 16 KB box further.
           umma_ts(tO[t], tS[t] + kk * 8, make_smem_desc(va + kk * 2048, 16384, 1024), idesc_pv,
@@ -340,7 +372,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         }
       };
 
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+      for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
         const WorkItem w = decode_item(p, item);
         const int n0 = w.n[0], n1 = w.n[1];
         const int nmax = max(n0, n1);
@@ -366,7 +398,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
                 mbar_wait(&v_full[vc % NS], (vc / NS) & 1);
                 ++vcnt_wait;
               }
-              mbar_wait(&p_full[1], pcnt[1] & 1);
+              if (!QH) mbar_wait(&p_full[1], pcnt[1] & 1);
               ++pcnt[1];
               tc_fence_after();
               issue_pv(1, vc % NS, j - 1 > 0);
@@ -390,7 +422,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
               mbar_wait(&v_full[vc % NS], (vc / NS) & 1);
               ++vcnt_wait;
             }
-            mbar_wait(&p_full[0], pcnt[0] & 1);
+            if (!QH) mbar_wait(&p_full[0], pcnt[0] & 1);
             ++pcnt[0];
             tc_fence_after();
             issue_pv(0, vc % NS, j > 0);
@@ -412,7 +444,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     uint8_t* stage = sQ + t * Cfg::TILE_BYTES;
     uint32_t item_cnt = 0, scnt = 0, ocnt = 0;
 
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+    for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
       const WorkItem w = decode_item(p, item);
       const int n = w.n[t];
       const long long qpos = w.qpos[t] + row;           // global position of this thread's query row
@@ -494,16 +526,24 @@ __global__ void __launch_bounds__(A_THREADS, 1)
             l1 += p1;
             l2 += p2;
             l3 += p3;
-            pk[i / 2] = PF16 ? pack_f16(p0, p1) : pack_bf16(p0, p1);
-            pk[i / 2 + 1] = PF16 ? pack_f16(p2, p3) : pack_bf16(p2, p3);
+            pk[i / 2] = pack_bf16(p0, p1);
+            pk[i / 2 + 1] = pack_bf16(p2, p3);
           }
           tmem_st16(tS + c * 16, pk);
+          if (QH) {
+            tmem_wait_st();          // (also covers the lazy O rescale before the first quarter)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_q[t * 4 + c]);
+          }
         }
         l += (l0 + l1) + (l2 + l3);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (!QH) {
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[t]);
+        }
       }
 
       // ---------------- epilogue: O / l -> bf16 -> smem (swizzled) -> TMA store; LSE ----------------
@@ -588,12 +628,8 @@ struct WorkItem2 {
 __device__ __forceinline__ WorkItem2 decode_item2(const AttnKParams& p, int item) {
   WorkItem2 w;
   const int G = p.hq / p.hkv;
-  const int g = item % G;
-  int r = item / G;
-  const int rank = r % p.n_qblk;
-  r /= p.n_qblk;
-  w.kvh = r % p.hkv;
-  w.b = r / p.hkv;
+  int g, rank;
+  split_item(p, item, w.b, w.kvh, rank, g);
   w.h = w.kvh * G + g;
   const int qblk = p.causal ? (p.n_qblk - 1 - rank) : rank;
   const int n_steps = (p.sk + A_BH - 1) / A_BH;
@@ -685,7 +721,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     if (lane == 0) {
       uint32_t item_cnt = 0, kcnt = 0, vcnt = 0;
       int ready_upto = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+      for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
         const WorkItem2 w = decode_item2(p, item);
         const int ntile = (max(w.n[0], w.n[1]) + 1) / 2;   // 128-row K/V tiles
         for (int t = 0; t < 2; ++t) {
@@ -731,7 +767,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
       uint32_t item_cnt = 0;
       uint32_t kbase = 0, vbase = 0;            // ring counters of this item's tile 0
       uint32_t scnt[2][2] = {{0, 0}, {0, 0}};   // completed uses of s_full / p_full [tile][buffer]
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+      for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
         const WorkItem2 w = decode_item2(p, item);
         const int nmax = max(w.n[0], w.n[1]);
         const int ntile = (nmax + 1) / 2;
@@ -814,7 +850,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     uint32_t scnt[2] = {0, 0};   // uses of s_full[t][b]
     uint32_t pv_base = 0;        // PV commits on o_done[t] before this item
 
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+    for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
       const WorkItem2 w = decode_item2(p, item);
       const int n = w.n[t];
       const long long qpos = w.qpos[t] + row;
@@ -972,7 +1008,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int D, bool PF16, bool CP, int VER>
+template <int D, bool QH, bool CP, int VER>
 static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_t s) {
   using Cfg = AttnCfg<D>;
   CUtensorMap tmQ, tmK, tmV, tmO;
@@ -1009,13 +1045,15 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
   p.kv_pos0 = a->kv_pos0;
   p.n_qblk = (int)((a->sq + 255) / 256);
   p.n_items = (int)(a->batch * a->hq * p.n_qblk);
+  // all kv heads' K and V fit comfortably in the 126 MB L2 -> global longest-first order
+  p.block_major = (a->causal && a->sk * a->hkv * a->d * 4 <= (64ll << 20)) ? 1 : 0;
   p.lse = a->lse;
   static bool attr_set = false;
   if (!attr_set) {
     if constexpr (VER == 2) {
       LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<D, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     } else {
-      LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, PF16, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
+      LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, QH, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     }
     attr_set = true;
   }
@@ -1029,7 +1067,7 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
   if constexpr (VER == 2)
     attn_fwd2_kernel<D, CP><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p, cpp);
   else
-    attn_fwd_kernel<D, PF16, CP><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p, cpp);
+    attn_fwd_kernel<D, QH, CP><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p, cpp);
   LV_CHECK_LAUNCH("attn_fwd_kernel");
   return LV_OK;
 }
@@ -1038,12 +1076,12 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
 
 using namespace lv;
 
-// LV_ATTN_VERSION=2 selects the double-buffered-S kernel (experimental: correct, currently slower);
-// default is the single-S-buffer kernel.
+// LV_ATTN_VERSION: 1 = single-S-buffer kernel (default), 2 = double-buffered-S kernel (correct, slower),
+// 3 = kernel 1 with the quarter-wise P hand-off.
 static int attn_version() {
   static const int v = [] {
     const char* e = getenv("LV_ATTN_VERSION");
-    return (e != nullptr && e[0] == '2') ? 2 : 1;
+    return (e != nullptr && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 1;
   }();
   return v;
 }
@@ -1076,6 +1114,10 @@ extern "C" int lv_attn_fwd(const lv_attn_params* a, lv_stream_t stream) {
   if (attn_version() == 2) {
     if (a->d == 128) return launch_attn<128, false, false, 2>(a, nullptr, s);
     return launch_attn<64, false, false, 2>(a, nullptr, s);
+  }
+  if (attn_version() == 3) {
+    if (a->d == 128) return launch_attn<128, true, false, 1>(a, nullptr, s);
+    return launch_attn<64, true, false, 1>(a, nullptr, s);
   }
   if (a->d == 128) return launch_attn<128, false, false, 1>(a, nullptr, s);
   return launch_attn<64, false, false, 1>(a, nullptr, s);
@@ -1119,6 +1161,7 @@ extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv
   k.v_full = reinterpret_cast<__nv_bfloat16*>(c->v_full);
   k.blk_flags = reinterpret_cast<uint32_t*>(c->blk_flags);
   if (attn_version() == 2) return launch_attn<128, false, true, 2>(a, &k, (cudaStream_t)stream);
+  if (attn_version() == 3) return launch_attn<128, true, true, 1>(a, &k, (cudaStream_t)stream);
   return launch_attn<128, false, true, 1>(a, &k, (cudaStream_t)stream);
 }
 

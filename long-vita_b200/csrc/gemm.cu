@@ -159,6 +159,64 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       tile_coords(tile, num_m, num_n, mb, nb);
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
+      if (act == 3) {
+        // Fused SwiGLU: W rows are interleaved (gate_i, up_i), so accumulator columns (2i, 2i+1) hold
+        // gate_i and up_i; out[:, i] = bf16(silu(bf16 gate)) * bf16(up) - the exact rounding sequence of
+        // the un-fused GEMM + lv_swiglu pair - and the stored tile is 128 columns wide.
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t packed[32];
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t r0[32], r1[32];
+            const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + as * G_BN + cc * 128 + hlf * 64;
+            tmem_ld32(taddr, r0);
+            tmem_ld32(taddr + 32, r1);
+            tmem_wait_ld();
+            if (cc == 1 && hlf == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&acc_empty[as]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float g0 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r0[j + 2 * e])));
+                const float u0 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r0[j + 2 * e + 1])));
+                const float g1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r1[j + 2 * e])));
+                const float u1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r1[j + 2 * e + 1])));
+                o[e] = __bfloat162float(__float2bfloat16_rn(__fdividef(g0, 1.f + __expf(-g0)))) * u0;
+                o[2 + e] = __bfloat162float(__float2bfloat16_rn(__fdividef(g1, 1.f + __expf(-g1)))) * u1;
+              }
+              packed[hlf * 16 + j / 4] = pack_bf16(o[0], o[1]);          // out cols hlf*32 + j/2 .. +1
+              packed[hlf * 16 + 8 + j / 4] = pack_bf16(o[2], o[3]);      // out cols hlf*32 + 16 + j/2 .. +1
+            }
+          }
+          uint8_t* stg = sC + (chunk_counter & 1) * G_C_BYTES;
+          if (epi_tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          named_bar_sync(1, 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(stg + off) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (epi_tid == 0) {
+            tma_store_2d(&tmC, stg, nb * (G_BN / 2) + cc * 64, mb * G_BM);
+            tma_store_commit();
+          }
+          ++chunk_counter;
+        }
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < G_BN / 64; ++c) {
         uint32_t r0[32], r1[32];
@@ -283,7 +341,7 @@ static int launch_gemm(const void* A, const void* W, const void* bias, void* C, 
     if (r) return r;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    const uint64_t dims[2] = {(uint64_t)(act == 3 ? N / 2 : N), (uint64_t)M};
     const uint64_t str[2] = {2, (uint64_t)ldc * 2};
     const uint32_t box[2] = {64, G_BM};
     int r = encode_tmap_bf16(&tmC, C, 2, dims, str, box, true);
@@ -314,9 +372,10 @@ int lv_gemm_bias_act(const void* A, const void* W, const void* bias, void* C, in
   LV_CHECK_ARG(M >= 0 && N > 0 && K > 0, "lv_gemm_bias_act: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   LV_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "lv_gemm_bias_act: dimension too large");
   LV_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "lv_gemm_bias_act: K=%lld and N=%lld must be multiples of 8", (long long)K, (long long)N);
-  LV_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0,
+  LV_CHECK_ARG(act >= 0 && act <= 3, "lv_gemm_bias_act: unknown activation %d", act);
+  LV_CHECK_ARG(lda >= K && ldw >= K && ldc >= (act == 3 ? N / 2 : N) && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0,
                "lv_gemm_bias_act: leading dimensions must be >= the row length and multiples of 8");
-  LV_CHECK_ARG(act >= 0 && act <= 2, "lv_gemm_bias_act: unknown activation %d", act);
+  LV_CHECK_ARG(act != 3 || (N % 16 == 0 && bias == nullptr), "lv_gemm_bias_act: fused SwiGLU needs N %% 16 == 0 and no bias");
   if (M == 0) return LV_OK;
   LV_BIND_DEVICE(A);
   return launch_gemm(A, W, bias, C, M, N, K, lda, ldw, ldc, act, (cudaStream_t)stream);

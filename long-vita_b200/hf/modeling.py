@@ -124,7 +124,8 @@ class DecoderLayer:
         self.bqkv = torch.cat([w[p + "self_attn.q_proj.bias"], w[p + "self_attn.k_proj.bias"],
                                w[p + "self_attn.v_proj.bias"]], dim=0).contiguous()
         self.wo = w[p + "self_attn.o_proj.weight"]
-        self.w_gate_up = torch.cat([w[p + "mlp.gate_proj.weight"], w[p + "mlp.up_proj.weight"]], dim=0).contiguous()
+        # rows interleaved (gate_i, up_i): SwiGLU runs in the GEMM epilogue, [T, 2I] never touches HBM
+        self.w_gate_up = ops.interleave_gate_up(w[p + "mlp.gate_proj.weight"], w[p + "mlp.up_proj.weight"])
         self.w_down = w[p + "mlp.down_proj.weight"]
         self.ln1 = w[p + "input_layernorm.weight"]
         self.ln2 = w[p + "post_attention_layernorm.weight"]
@@ -148,7 +149,7 @@ class DecoderLayer:
         att = ops.attention_fwd(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), causal=True, **attn_kwargs)
         o = ops.linear(att.view(T, hq * d), self.wo)
         h, x = ops.rmsnorm(o, self.ln2, cfg.rms_norm_eps, residual=x)
-        a = ops.swiglu(ops.linear(h, self.w_gate_up))
+        a = ops.linear(h, self.w_gate_up, act="swiglu")
         return x, ops.linear(a, self.w_down)
 
 

@@ -387,7 +387,7 @@ def row_scatter_zero(x: torch.Tensor, idx: torch.Tensor, n_rows_out: int):
 # ------------------------------------------------------------------------------------------------
 # dense linears
 # ------------------------------------------------------------------------------------------------
-_ACT = {None: 0, "none": 0, "gelu": 1, "gelu_tanh": 2}
+_ACT = {None: 0, "none": 0, "gelu": 1, "gelu_tanh": 2, "swiglu": 3}
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
@@ -402,8 +402,9 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     if weight.stride(1) != 1:
         weight = weight.contiguous()
     M = x2.shape[0]
+    n_out = N // 2 if act == "swiglu" else N      # fused SwiGLU: weight rows interleaved (gate_i, up_i)
     if out is None:
-        out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+        out = torch.empty((M, n_out), dtype=torch.bfloat16, device=x.device)
     ev0 = _TIMER.start() if _TIMER is not None else None
     _lib.check(
         _lib.lib().lv_gemm_bias_act(x2.data_ptr(), weight.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, x2.stride(0),
@@ -412,7 +413,40 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     )
     if ev0 is not None:
         _TIMER.stop("gemm_bf16", 2.0 * M * N * K, ev0)
-    return out.view(*x.shape[:-1], N)
+    return out.view(*x.shape[:-1], n_out)
+
+
+def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor:
+    """[I, H] gate and up projection weights -> [2I, H] with rows (gate_0, up_0, gate_1, up_1, ...):
+    the operand layout of linear(..., act="swiglu") (one-time, at load)."""
+    return torch.stack([gate_w, up_w], dim=1).reshape(2 * gate_w.shape[0], gate_w.shape[1]).contiguous()
+
+
+def masked_linear(h: torch.Tensor, weight: torch.Tensor, logit_mask: torch.Tensor, bias: Optional[torch.Tensor] = None):
+    """Logit-masked LM head forward: rows of h [s, b, c] selected by logit_mask [b, s] -> [M, b, vocab]
+    (LinearWithGradAccumulationAndAsyncCommunication.forward with logit_mask,
+    long_vita_megatron/core/tensor_parallel/layers.py:402-409).  b = 1 (the reference's setting when
+    logit_mask is used: micro-batch 1).  The row indices are computed by torch (host-side index op)."""
+    _need_cuda_bf16(h, weight, bias)
+    s, b, c = h.shape
+    if b != 1:
+        raise NotImplementedError("masked_linear: micro-batch 1")
+    idx = logit_mask.reshape(-1).nonzero().view(-1)
+    sel = row_gather(h.reshape(s, c), idx)
+    return linear(sel, weight, bias).view(idx.numel(), 1, -1)
+
+
+def masked_linear_dgrad(grad_out: torch.Tensor, weight: torch.Tensor, logit_mask: torch.Tensor):
+    """dX of masked_linear: masked_scatter(zeros[s, b, c], dY @ W) (layers.py:443-451).  `weight` is
+    [vocab, c]; the GEMM needs its transpose as the [N, K] operand, materialised by the caller once
+    (weights are frozen in the reference's use of this path: linear_with_frozen_weight, :288-363)."""
+    _need_cuda_bf16(grad_out, weight)
+    m = grad_out.shape[0]
+    s = logit_mask.shape[-1]
+    wt = weight.t().contiguous()                      # [c, vocab] = the [N, K] operand of dY @ W
+    gi = linear(grad_out.reshape(m, -1), wt)          # [M, c]
+    idx = logit_mask.reshape(-1).nonzero().view(-1)
+    return row_scatter_zero(gi, idx, s).view(s, 1, -1)
 
 
 def patch_embed(images: torch.Tensor, w_pad: torch.Tensor, bias: Optional[torch.Tensor], cls: torch.Tensor,

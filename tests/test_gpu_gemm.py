@@ -75,3 +75,37 @@ def test_patch_embed(L):
     assert rel_fro(out, ref) < 3e-3, rel_fro(out, ref)
     # class-token row is an exact bf16 add
     assert torch.equal(out[:, 0].cpu(), (cls + pos[:, :1]).expand(n, 1, C)[:, 0])
+
+
+def test_logit_masked_lm_head_forward_and_dgrad(L):
+    """a12: masked_select + GEMM (layers.py:402-409) and its input gradient (layers.py:443-451)."""
+    g = seeded(14)
+    s, c, vocab = 700, 640, 2048
+    h = randn_bf16((s, 1, c), g)
+    w = randn_bf16((vocab, c), g, 0.05)
+    mask = torch.rand(1, s, generator=g) < 0.05
+    mask[0, -1] = True
+    out = L.masked_linear(h.cuda(), w.cuda(), mask.cuda())
+    ref = O.masked_linear_fwd(h.float(), w.float(), mask)
+    assert out.shape == ref.shape
+    assert rel_fro(out, ref.to(torch.bfloat16)) < 1e-3          # vs the oracle rounded once to bf16, like the other GEMM tests
+    go = randn_bf16(tuple(ref.shape), g)
+    gx = L.masked_linear_dgrad(go.cuda(), w.cuda(), mask.cuda())
+    gx_ref, _ = O.masked_linear_bwd(go.float(), h.float(), w.float(), mask)
+    assert gx.shape == (s, 1, c)
+    assert rel_fro(gx, gx_ref.to(torch.bfloat16)) < 1e-3
+    # rows outside the mask are exactly zero (masked_scatter into zeros)
+    assert torch.equal(gx.cpu()[~mask[0]], torch.zeros_like(gx.cpu()[~mask[0]]))
+
+
+def test_gemm_fused_swiglu_epilogue_is_bit_exact_with_unfused_pair(L):
+    g = seeded(15)
+    M, H, I = 700, 1024, 2304
+    x = randn_bf16((M, H), g)
+    gate, up = randn_bf16((I, H), g, 0.05), randn_bf16((I, H), g, 0.05)
+    unfused = L.swiglu(L.linear(x.cuda(), torch.cat([gate, up]).cuda()))
+    fused = L.linear(x.cuda(), L.interleave_gate_up(gate.cuda(), up.cuda()), act="swiglu")
+    assert fused.shape == (M, I)
+    assert torch.equal(fused, unfused)
+    ref = O.swiglu(ref_linear(x, torch.cat([gate, up])))
+    assert rel_fro(fused, ref) < 1.5e-3

@@ -90,3 +90,59 @@ def test_intern_inner_attn_replacement(lib_built):
     assert _excess(out, ref) < 2e-3
     with pytest.raises(AssertionError):
         B200FlashAttention()(qkv.float().cuda())
+
+
+def test_whole_layer_spec_module_matches_oracle_decoder_layer(lib_built):
+    """B2: the `--spec` layer with TE state-dict names and Megatron's grouped QKV layout."""
+    from types import SimpleNamespace
+
+    from long_vita_b200.config import LongVITAConfig
+    from long_vita_b200.megatron import stub
+    from long_vita_b200.megatron.transformer_layer import B200TransformerLayer, get_b200_layer_spec
+    from long_vita_b200.weights import llm_layer_weights
+    from oracle import model as OM
+
+    cfg = LongVITAConfig.tiny(layers=1)
+    w = llm_layer_weights(cfg, 0, seed=5, dtype=torch.bfloat16, perturb=True)
+    mcfg = SimpleNamespace(hidden_size=cfg.hidden_size, num_attention_heads=cfg.num_attention_heads,
+                           num_query_groups=cfg.num_key_value_heads, kv_channels=cfg.head_dim,
+                           ffn_hidden_size=cfg.intermediate_size, layernorm_epsilon=cfg.rms_norm_eps,
+                           hidden_dropout=0.0, attention_dropout=0.0, params_dtype=torch.bfloat16)
+    spec = get_b200_layer_spec()
+    layer = stub.build_module(spec, config=mcfg, layer_number=1)
+    assert isinstance(layer, B200TransformerLayer)
+    names = set(layer.state_dict().keys())
+    assert {"self_attention.linear_qkv.layer_norm_weight", "self_attention.linear_qkv.weight",
+            "self_attention.linear_qkv.bias", "self_attention.linear_proj.weight", "mlp.linear_fc1.layer_norm_weight",
+            "mlp.linear_fc1.weight", "mlp.linear_fc2.weight"} == names
+    # HF -> mcore grouped layout (tools/hf2mcore_long_vita.py:599-613)
+    p = "model.layers.0."
+    ng, g, hn, h = cfg.num_key_value_heads, cfg.num_attention_heads // cfg.num_key_value_heads, cfg.head_dim, cfg.hidden_size
+    qw = w[p + "self_attn.q_proj.weight"].view(ng, g, hn, h)
+    kw = w[p + "self_attn.k_proj.weight"].view(ng, 1, hn, h)
+    vw = w[p + "self_attn.v_proj.weight"].view(ng, 1, hn, h)
+    qb = w[p + "self_attn.q_proj.bias"].view(ng, g, hn)
+    kb = w[p + "self_attn.k_proj.bias"].view(ng, 1, hn)
+    vb = w[p + "self_attn.v_proj.bias"].view(ng, 1, hn)
+    sd = {
+        "self_attention.linear_qkv.layer_norm_weight": w[p + "input_layernorm.weight"],
+        "self_attention.linear_qkv.weight": torch.cat([qw, kw, vw], dim=1).reshape(-1, h),
+        "self_attention.linear_qkv.bias": torch.cat([qb, kb, vb], dim=1).reshape(-1),
+        "self_attention.linear_proj.weight": w[p + "self_attn.o_proj.weight"],
+        "mlp.linear_fc1.layer_norm_weight": w[p + "post_attention_layernorm.weight"],
+        "mlp.linear_fc1.weight": torch.cat([w[p + "mlp.gate_proj.weight"], w[p + "mlp.up_proj.weight"]], dim=0),
+        "mlp.linear_fc2.weight": w[p + "mlp.down_proj.weight"],
+    }
+    layer.load_state_dict({k: v.cuda() for k, v in sd.items()}, strict=True)
+    s = 515
+    g_ = seeded(6)
+    x = randn_bf16((s, 1, h), g_)
+    inv = O.rope_inv_freq(hn, cfg.rope_theta)
+    freqs = torch.outer(torch.arange(s).float(), inv)
+    emb = torch.cat((freqs, freqs), dim=-1)[:, None, None, :]            # Megatron RotaryEmbedding.forward output
+    out, ctx = layer(hidden_states=x.cuda(), attention_mask=None, context=None, context_mask=None,
+                     rotary_pos_emb=emb.cuda(), inference_params=None, packed_seq_params=None)
+    assert ctx is None and out.shape == (s, 1, h)
+    cos, sin = O.rope_tables(torch.arange(s), inv, torch.bfloat16)
+    ref = OM.decoder_layer(cfg, OM.cast_weights(w, torch.float32), 0, x[:, 0].float(), cos.float(), sin.float())
+    assert rel_fro(out[:, 0], ref) < 4e-3, rel_fro(out[:, 0], ref)
