@@ -241,7 +241,9 @@ int lv_gemm_bias_act(const void* A, const void* W, const void* bias, void* C, in
  * out[n, 0, :] = cls + pos[0]; out[n, 1 + p, :] = bf16(W . patch(n, p) + bias) + pos[1 + p].
  * images bf16 [n, 3, img, img]; W bf16 [C, Kpad] = the conv weight flattened to [C, 3*ps*ps] and
  * zero-padded per row to Kpad = 3*ps*ps rounded up to a multiple of 64 (done once at load time);
- * out bf16 [n, 1 + (img/ps)^2, C].  `ws` is caller workspace of lv_patch_embed_ws_bytes() bytes
+ * out bf16 [n, 1 + (img/ps)^2, C].  cls == NULL selects the class-token-free form of SigLIP
+ * (long_vita_megatron/core/models/vision/siglip_vit_model.py:165-176): out [n, (img/ps)^2, C],
+ * out[n, p] = bf16(W . patch + bias) + pos[p].  `ws` is caller workspace of lv_patch_embed_ws_bytes() bytes
  * (the im2col matrix and the un-offset GEMM result). */
 int64_t lv_patch_embed_ws_bytes(int64_t n, int64_t img, int64_t ps, int64_t C);
 int lv_patch_embed(const void* images, const void* W, const void* bias, const void* cls, const void* pos,

@@ -315,10 +315,12 @@ __global__ void __launch_bounds__(128) add_cls_pos_kernel(const __nv_bfloat16* _
                                                           const __nv_bfloat16* __restrict__ cls,
                                                           const __nv_bfloat16* __restrict__ pos,
                                                           __nv_bfloat16* __restrict__ out, int64_t n, int P, int C) {
-  const int64_t tok = blockIdx.x;  // n * (P + 1)
-  const int64_t im = tok / (P + 1);
-  const int t = (int)(tok % (P + 1));
-  const __nv_bfloat16* src = t == 0 ? cls : tmp + (im * P + (t - 1)) * (int64_t)C;
+  // cls == nullptr: no class token (SigLIP, siglip_vit_model.py:165-176): out[n, p] = tmp[n*P + p] + pos[p]
+  const int hc = cls != nullptr ? 1 : 0;
+  const int64_t tok = blockIdx.x;  // n * (P + hc)
+  const int64_t im = tok / (P + hc);
+  const int t = (int)(tok % (P + hc));
+  const __nv_bfloat16* src = (hc && t == 0) ? cls : tmp + (im * P + (t - hc)) * (int64_t)C;
   for (int c = threadIdx.x; c < C; c += blockDim.x)
     out[tok * C + c] = __float2bfloat16_rn(__bfloat162float(src[c]) + __bfloat162float(pos[(int64_t)t * C + c]));
 }
@@ -389,7 +391,7 @@ int64_t lv_patch_embed_ws_bytes(int64_t n, int64_t img, int64_t ps, int64_t C) {
 
 int lv_patch_embed(const void* images, const void* W, const void* bias, const void* cls, const void* pos, void* out,
                    void* ws, int64_t n, int64_t img, int64_t ps, int64_t C, lv_stream_t stream) {
-  LV_CHECK_ARG(images && W && cls && pos && out && ws, "lv_patch_embed: null pointer");
+  LV_CHECK_ARG(images && W && pos && out && ws, "lv_patch_embed: null pointer");
   LV_CHECK_ARG(img > 0 && ps > 0 && img % ps == 0 && C % 8 == 0, "lv_patch_embed: bad geometry img=%lld ps=%lld C=%lld", (long long)img, (long long)ps, (long long)C);
   if (n == 0) return LV_OK;
   LV_BIND_DEVICE(images);
@@ -404,7 +406,7 @@ int lv_patch_embed(const void* images, const void* W, const void* bias, const vo
   LV_CHECK_LAUNCH("im2col_patch_kernel");
   int r = launch_gemm(col, W, bias, tmp, n * P, C, kpad, kpad, kpad, C, 0, s);
   if (r) return r;
-  add_cls_pos_kernel<<<(unsigned)(n * (P + 1)), 128, 0, s>>>(tmp, reinterpret_cast<const __nv_bfloat16*>(cls),
+  add_cls_pos_kernel<<<(unsigned)(n * (P + (cls != nullptr ? 1 : 0))), 128, 0, s>>>(tmp, reinterpret_cast<const __nv_bfloat16*>(cls),
                                                            reinterpret_cast<const __nv_bfloat16*>(pos),
                                                            reinterpret_cast<__nv_bfloat16*>(out), n, (int)P, (int)C);
   LV_CHECK_LAUNCH("add_cls_pos_kernel");

@@ -460,10 +460,10 @@ def patch_embed(images: torch.Tensor, w_pad: torch.Tensor, bias: Optional[torch.
     P = (size // patch) ** 2
     ws_bytes = int(_lib.lib().lv_patch_embed_ws_bytes(n, size, patch, Cc))
     ws = torch.empty(ws_bytes // 2, dtype=torch.bfloat16, device=images.device)
-    out = torch.empty((n, P + 1, Cc), dtype=torch.bfloat16, device=images.device)
+    out = torch.empty((n, P + (0 if cls is None else 1), Cc), dtype=torch.bfloat16, device=images.device)
     _lib.check(
         _lib.lib().lv_patch_embed(images.data_ptr(), w_pad.contiguous().data_ptr(), _ptr(bias),
-                                  cls.contiguous().data_ptr(), pos.contiguous().data_ptr(), out.data_ptr(),
+                                  None if cls is None else cls.contiguous().data_ptr(), pos.contiguous().data_ptr(), out.data_ptr(),
                                   ws.data_ptr(), n, size, patch, Cc, _stream()),
         "lv_patch_embed",
     )

@@ -131,3 +131,27 @@ def long_vita_forward(cfg, w, input_ids: torch.Tensor, images: Optional[torch.Te
 
 def cast_weights(w: Dict[str, torch.Tensor], dtype) -> Dict[str, torch.Tensor]:
     return {k: v.to(dtype) for k, v in w.items()}
+
+
+def siglip_forward(cfg, w: Dict[str, torch.Tensor], images: torch.Tensor, prefix: str = ""):
+    """SigLIPViTModel.forward (long_vita_megatron/core/models/vision/siglip_vit_model.py:165-228) with the
+    block of :29-86 and the geometry of pretrain_long_vita.py:268-307.  `cfg` has hidden_size,
+    num_attention_heads, kv_channels, num_layers, patch_dim, layernorm_epsilon.  linear_qkv rows are
+    Megatron's per-head interleave [head, (q, k, v), hn]."""
+    H, hn, C = cfg.num_attention_heads, cfg.kv_channels, cfg.hidden_size
+    x = F.conv2d(images, w[prefix + "conv1.weight"], w[prefix + "conv1.bias"], stride=cfg.patch_dim)
+    x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
+    x = x + w[prefix + "position_embeddings.weight"].to(x.dtype)[None]
+    n, S, _ = x.shape
+    for i in range(cfg.num_layers):
+        p = f"{prefix}decoder.layers.{i}."
+        y = F.layer_norm(x, (C,), w[p + "input_layernorm.weight"], w[p + "input_layernorm.bias"], cfg.layernorm_epsilon)
+        qkv = F.linear(y, w[p + "self_attention.linear_qkv.weight"], w[p + "self_attention.linear_qkv.bias"])
+        qkv = qkv.view(n, S, H, 3, hn)
+        att, _ = O.attention(qkv[:, :, :, 0], qkv[:, :, :, 1], qkv[:, :, :, 2], causal=False, scale=hn ** -0.5)
+        att = att.to(x.dtype).reshape(n, S, H * hn)
+        x = x + F.linear(att, w[p + "self_attention.linear_proj.weight"], w[p + "self_attention.linear_proj.bias"])
+        y = F.layer_norm(x, (C,), w[p + "pre_mlp_layernorm.weight"], w[p + "pre_mlp_layernorm.bias"], cfg.layernorm_epsilon)
+        f = F.gelu(F.linear(y, w[p + "mlp.linear_fc1.weight"], w[p + "mlp.linear_fc1.bias"]), approximate="tanh")
+        x = x + F.linear(f, w[p + "mlp.linear_fc2.weight"], w[p + "mlp.linear_fc2.bias"])
+    return x

@@ -103,3 +103,32 @@ def test_signature_guards(setup):
         model(input_ids=ids, use_cache=True)
     with pytest.raises(ValueError):
         model(input_ids=None)
+
+
+def test_siglip_tower_matches_oracle(lib_built):
+    """a9: SigLIP geometry (head_dim 72, no class token, tanh-GELU) on a 2-layer, 2-head slice."""
+    from long_vita_b200.hf.siglip import SigLIPConfig, SigLIPViTModel
+
+    cfg = SigLIPConfig(hidden_size=144, ffn_hidden_size=304, num_layers=2, num_attention_heads=2, kv_channels=72)
+    g = torch.Generator().manual_seed(21)
+
+    def rn(*shape, std=0.05):
+        return (torch.randn(*shape, generator=g) * std).to(torch.bfloat16)
+
+    C, I = cfg.hidden_size, cfg.ffn_hidden_size
+    w = {"conv1.weight": rn(C, 3, 14, 14), "conv1.bias": rn(C), "position_embeddings.weight": rn(cfg.num_patches, C, std=1.0)}
+    for i in range(cfg.num_layers):
+        p = f"decoder.layers.{i}."
+        w.update({
+            p + "input_layernorm.weight": (1 + rn(C)).to(torch.bfloat16), p + "input_layernorm.bias": rn(C),
+            p + "self_attention.linear_qkv.weight": rn(3 * C, C), p + "self_attention.linear_qkv.bias": rn(3 * C),
+            p + "self_attention.linear_proj.weight": rn(C, C), p + "self_attention.linear_proj.bias": rn(C),
+            p + "pre_mlp_layernorm.weight": (1 + rn(C)).to(torch.bfloat16), p + "pre_mlp_layernorm.bias": rn(C),
+            p + "mlp.linear_fc1.weight": rn(I, C), p + "mlp.linear_fc1.bias": rn(I),
+            p + "mlp.linear_fc2.weight": rn(C, I), p + "mlp.linear_fc2.bias": rn(C),
+        })
+    images = torch.randn(2, 3, 448, 448, generator=g).to(torch.bfloat16)
+    out = SigLIPViTModel(cfg, {k: v.cuda() for k, v in w.items()})(images.cuda())
+    ref = OM.siglip_forward(cfg, OM.cast_weights(w, torch.float32), images.float())
+    assert out.shape == (2, 1024, C)
+    assert rel_fro(out, ref) < 6e-3, rel_fro(out, ref)
