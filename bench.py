@@ -175,6 +175,17 @@ def main():
                          "the printed line is then marked as outside the timing contract")
     ap.add_argument("--layers", type=int, default=None, help="debug: fewer decoder layers (number is then INVALID)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything libraries print meanwhile (e.g. NCCL's
+    # "NCCL version ..." banner, written to fd 1 from C) is routed to stderr until the line is emitted
+    sys.stdout.flush()
+    _stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(_stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,7 +223,7 @@ def main():
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     import torch
@@ -351,7 +362,7 @@ def main():
         v, m, desc = cpu_reference_sample(cfg, S, args.frames, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
                                 "seconds_measured": m}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
