@@ -259,24 +259,9 @@ class ContextParallelRunner:
                               sh.src_idx if feat is not None else None)
         cos, sin = ops.rope_table(sh.position_ids.to(torch.int64), m.inv_freq)
         T = x.shape[0]
-        hq, hkv, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
         delta = None
         for layer in m.layers:
-            if delta is None:
-                h = ops.rmsnorm(x, layer.ln1, cfg.rms_norm_eps)
-            else:
-                h, x = ops.rmsnorm(delta, layer.ln1, cfg.rms_norm_eps, residual=x)
-            qkv = ops.linear(h, layer.wqkv, layer.bqkv, out=ctx.qkv_buffer())
-            qkv = qkv.view(T, -1)
-            q = qkv[:, : hq * d].view(T, hq, d)
-            k = qkv[:, hq * d : (hq + hkv) * d].view(T, hkv, d)
-            ops.rope(q, cos, sin, out=q)
-            ops.rope(k, cos, sin, out=k)
-            att = ctx.attention()
-            o = ops.linear(att, layer.wo)
-            h, x = ops.rmsnorm(o, layer.ln2, cfg.rms_norm_eps, residual=x)
-            a = ops.linear(h, layer.w_gate_up, act="swiglu")
-            delta = ops.linear(a, layer.w_down)
+            x, delta = layer.forward_cp(x, delta, cos, sin, ctx)
         h, _ = ops.rmsnorm(delta, m.norm_w, cfg.rms_norm_eps, residual=x)
         # logit mask: each rank projects its own last row; the globally-last token lives on rank 0
         # (chunk 2cp-1), generation.py:141-165

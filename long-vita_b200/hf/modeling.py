@@ -152,6 +152,27 @@ class DecoderLayer:
         a = ops.linear(h, self.w_gate_up, act="swiglu")
         return x, ops.linear(a, self.w_down)
 
+    def forward_cp(self, x: torch.Tensor, delta: Optional[torch.Tensor], cos, sin, ctx) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The same layer on this rank's zig-zag shard (`ctx` is the rank's cp.CPContext): the QKV GEMM
+        writes straight into the peer-mapped buffer, RoPE runs in place there, and the fused kernel
+        pulls the other ranks' K/V itself (lv_attn_cp_fwd)."""
+        cfg = self.cfg
+        T = x.shape[0]
+        hq, hkv, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        if delta is None:
+            h = ops.rmsnorm(x, self.ln1, cfg.rms_norm_eps)
+        else:
+            h, x = ops.rmsnorm(delta, self.ln1, cfg.rms_norm_eps, residual=x)
+        qkv = ops.linear(h, self.wqkv, self.bqkv, out=ctx.qkv_buffer()).view(T, -1)
+        q = qkv[:, : hq * d].view(T, hq, d)
+        k = qkv[:, hq * d : (hq + hkv) * d].view(T, hkv, d)
+        ops.rope(q, cos, sin, out=q)
+        ops.rope(k, cos, sin, out=k)
+        o = ops.linear(ctx.attention(), self.wo)
+        h, x = ops.rmsnorm(o, self.ln2, cfg.rms_norm_eps, residual=x)
+        a = ops.linear(h, self.w_gate_up, act="swiglu")
+        return x, ops.linear(a, self.w_down)
+
 
 class LongVITAModel:
     def __init__(self, cfg: LongVITAConfig, weights: Dict[str, torch.Tensor]):

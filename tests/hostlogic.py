@@ -1,0 +1,138 @@
+"""Host-logic harness for CPU tests - TEST INFRASTRUCTURE ONLY, never imported by the product package.
+
+The Python layers above the C ABI (weight re-layouts, index translation, argument handling, the
+order in which operators are composed) are host logic: it can be wrong while every kernel is right.
+To check it on a box without a GPU, `oracle_ops()` temporarily replaces the operator wrappers of
+`long_vita_b200.ops` (each of which normally calls liblvb200.so and refuses non-CUDA tensors) by the
+CPU oracle restatements with the same signatures.  What such a test proves is the composition - it
+says nothing about the kernels, whose parity tests are the `-m gpu` files and run the real library.
+Outside this context manager the product path is untouched and still fails loudly without CUDA.
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+
+import torch
+import torch.nn.functional as F
+
+from oracle import ops as O
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _attention_fwd(q, k, v, *, causal, scale=None, layout="bshd", return_lse=False, q_seg_len=None, q_seg_pos=None,
+                   kv_pos0=0, out=None):
+    perm = {"bshd": (0, 1, 2, 3), "sbhd": (1, 0, 2, 3), "bhsd": (0, 2, 1, 3)}[layout]
+    qv, kv, vv = (t.permute(perm) for t in (q, k, v))
+    sq, sk = qv.shape[1], kv.shape[1]
+    q_pos = None
+    if q_seg_len is not None and q_seg_pos is not None:
+        q_pos = torch.cat([torch.arange(q_seg_len) + q_seg_pos[i] for i in range(sq // q_seg_len)])
+    elif q_seg_pos is not None:
+        q_pos = torch.arange(sq) + q_seg_pos[0]
+    o, lse = O.attention(qv, kv, vv, causal=causal, scale=scale, q_pos=q_pos, kv_pos=torch.arange(sk) + kv_pos0)
+    inv = [perm.index(i) for i in range(4)]
+    o = _bf(o).permute(inv)
+    if out is not None:
+        out.copy_(o)
+        o = out
+    return (o, lse) if return_lse else o
+
+
+def _rmsnorm(x, weight, eps=1e-6, residual=None):
+    if residual is None:
+        return O.rmsnorm(x, weight, eps)
+    s = _bf(x.float() + residual.float())
+    return O.rmsnorm(s, weight, eps), s
+
+
+def _rope_table(pos, inv_freq):
+    return O.rope_tables(pos.view(-1), inv_freq, torch.bfloat16)
+
+
+def _rope(x, cos, sin, out=None):
+    y = _bf(x.float() * cos.float()[:, None, :] +
+            torch.cat((-x.float()[..., x.shape[-1] // 2:], x.float()[..., : x.shape[-1] // 2]), -1) * sin.float()[:, None, :])
+    if out is None:
+        return y
+    out.copy_(y)
+    return out
+
+
+def _linear(x, weight, bias=None, act=None, out=None):
+    y = x.float().reshape(-1, x.shape[-1]) @ weight.float().t()
+    if bias is not None:
+        y = y + bias.float()
+    if act == "gelu":
+        y = F.gelu(y)
+    elif act == "gelu_tanh":
+        y = F.gelu(y, approximate="tanh")
+    elif act == "swiglu":                      # rows interleaved (gate_i, up_i)
+        y = F.silu(_bf(y[:, 0::2]).float()) * _bf(y[:, 1::2]).float()
+    y = _bf(y)
+    if out is not None:
+        out.view(y.shape).copy_(y)
+        y = out
+    return y.view(*x.shape[:-1], y.shape[-1])
+
+
+def _pixel_shuffle(x, hw, has_cls):
+    n, _, c = x.shape
+    t = x[:, 1:] if has_cls else x
+    return O.pixel_shuffle_half(t.reshape(n, hw, hw, c)).reshape(n, (hw // 2) ** 2, 4 * c)
+
+
+def _patch_embed(images, w_pad, bias, cls, pos, patch):
+    C = w_pad.shape[0]
+    w = w_pad[:, : 3 * patch * patch].reshape(C, 3, patch, patch)
+    pe = F.conv2d(images.float(), w.float(), None if bias is None else bias.float(), stride=patch).flatten(2).transpose(1, 2)
+    if cls is not None:
+        pe = torch.cat([cls.float().reshape(1, 1, -1).expand(pe.shape[0], 1, -1), pe], dim=1)
+    return _bf(pe + pos.float().reshape(1, -1, C))
+
+
+def _row_scatter_zero(x, idx, n_rows_out):
+    out = torch.zeros((n_rows_out, x.shape[1]), dtype=x.dtype)
+    out[idx.view(-1)] = x
+    return out
+
+
+SUBSTITUTES = {
+    "attention_fwd": _attention_fwd,
+    "rmsnorm": _rmsnorm,
+    "layernorm": lambda x, w, b, eps=1e-6: O.layernorm(x, w, b, eps),
+    "rope_table": _rope_table,
+    "rope": _rope,
+    "swiglu": lambda gu: _bf(O.swiglu(gu.float())),
+    "bias_gelu": lambda x, bias=None, approximate="none": _bf(O.bias_gelu(x.float(), None if bias is None else bias.float(), approximate)),
+    "ls_residual": lambda x, y, ls=None, bias=None: _bf(O.ls_residual(x.float(), y.float(), None if ls is None else ls.float(),
+                                                                         None if bias is None else bias.float())),
+    "pixel_shuffle": _pixel_shuffle,
+    "embed_scatter": lambda ids, table, feat=None, dst_idx=None, src_idx=None: O.embed_scatter(ids, table, feat, dst_idx, src_idx),
+    "row_gather": lambda x, idx: x[idx.view(-1)].clone(),
+    "row_scatter_zero": _row_scatter_zero,
+    "linear": _linear,
+    "patch_embed": _patch_embed,
+    # composite wrappers (masked_linear, masked_linear_dgrad) keep their own host logic and only lose
+    # the "must be a CUDA tensor" guard
+    "_need_cuda_bf16": lambda *ts: None,
+    "_need_cuda": lambda t, dtype: None,
+}
+
+
+@contextlib.contextmanager
+def oracle_ops():
+    """Within the block, long_vita_b200.ops.<op> are the CPU oracle restatements (see module doc)."""
+    from long_vita_b200 import ops
+
+    saved = {name: getattr(ops, name) for name in SUBSTITUTES}
+    try:
+        for name, fn in SUBSTITUTES.items():
+            setattr(ops, name, fn)
+        yield ops
+    finally:
+        for name, fn in saved.items():
+            setattr(ops, name, fn)

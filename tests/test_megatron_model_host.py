@@ -1,0 +1,296 @@
+"""CPU tests of the host logic around the Megatron surface:
+
+* `megatron.checkpoint`: the mcore <-> HF weight layouts are bit-exact permutations, checked against
+  an independent restatement of the index description in tools/hf2mcore_long_vita.py:397-414, 488-504.
+* `megatron.gpt_vl_model.B200GPTVLModel.forward`: argument handling, the three embedding merge
+  modes, logit_mask, labels / loss, `inference_params` overrides - with the operator wrappers
+  replaced by the CPU oracle (tests/hostlogic.py), against oracle.model.long_vita_forward.
+  This checks composition and indexing only; kernel parity is the `-m gpu` suite.
+"""
+import types
+
+import pytest
+import torch
+
+from long_vita_b200.config import LongVITAConfig
+from long_vita_b200.megatron import checkpoint as ck
+from long_vita_b200.weights import synthetic_state_dict
+from oracle import model as OM
+from tests.hostlogic import oracle_ops
+from tests.util import rel_fro
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    cfg = LongVITAConfig.tiny(layers=2, vit_layers=1)
+    hf = synthetic_state_dict(cfg, seed=77, dtype=torch.bfloat16, perturb=True)
+    return cfg, hf, ck.hf_to_mcore(hf, cfg)
+
+
+def test_checkpoint_roundtrip_is_bit_exact(tiny):
+    cfg, hf, mc = tiny
+    back = ck.mcore_to_hf(mc, cfg)
+    assert set(back) == set(hf)
+    for k in hf:
+        assert back[k].shape == hf[k].shape and torch.equal(back[k], hf[k]), k
+    again = ck.hf_to_mcore(back, cfg)
+    assert set(again) == set(mc) and all(torch.equal(again[k], mc[k]) for k in mc)
+
+
+def test_vit_qkv_index_matches_the_scripts_loops():
+    # hf2mcore_long_vita.py:397-414 written out as the script does: q rows of every head, then k, then v
+    heads, hn = 16, 64
+    idx = []
+    for part in range(3):
+        for i in range(heads):
+            lb = i * hn * 3 + hn * part
+            idx.append(torch.arange(lb, lb + hn))
+    assert torch.equal(ck.vit_qkv_index(heads, hn), torch.cat(idx))
+
+
+def test_llm_grouped_qkv_layout(tiny):
+    cfg, hf, mc = tiny
+    ng, np_, hn, H = cfg.num_key_value_heads, cfg.num_attention_heads, cfg.head_dim, cfg.hidden_size
+    w = mc["decoder.layers.0.self_attention.linear_qkv.weight"]
+    assert w.shape == ((np_ + 2 * ng) * hn, H)
+    # independent statement of :488-498: view(ng, -1, hn, H), split [np/ng, 1, 1] along dim 1
+    q, k, v = torch.split(w.view(ng, -1, hn, H), [np_ // ng, 1, 1], dim=1)
+    assert torch.equal(q.reshape(-1, H), hf["model.layers.0.self_attn.q_proj.weight"])
+    assert torch.equal(k.reshape(-1, H), hf["model.layers.0.self_attn.k_proj.weight"])
+    assert torch.equal(v.reshape(-1, H), hf["model.layers.0.self_attn.v_proj.weight"])
+    b = mc["decoder.layers.0.self_attention.linear_qkv.bias"].view(ng, -1)
+    qb, kb, vb = torch.split(b, [H // ng, hn, hn], dim=1)                      # :495-498
+    assert torch.equal(qb.reshape(-1), hf["model.layers.0.self_attn.q_proj.bias"])
+    assert torch.equal(kb.reshape(-1), hf["model.layers.0.self_attn.k_proj.bias"])
+    assert torch.equal(vb.reshape(-1), hf["model.layers.0.self_attn.v_proj.bias"])
+    fc1 = mc["decoder.layers.0.mlp.linear_fc1.weight"]
+    g, u = torch.split(fc1, cfg.intermediate_size)                             # :502-504
+    assert torch.equal(g, hf["model.layers.0.mlp.gate_proj.weight"]) and torch.equal(u, hf["model.layers.0.mlp.up_proj.weight"])
+
+
+def _inputs(cfg, s=300, n_img=1, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, cfg.vocab_size, (1, s), generator=g)
+    images = torch.randn(n_img, 3, 448, 448, generator=g).to(torch.bfloat16)
+    idx_s = torch.stack([torch.arange(7 + i * 270, 7 + i * 270 + 256) for i in range(n_img)])
+    return ids, images, torch.stack([torch.zeros_like(idx_s), idx_s])
+
+
+@pytest.fixture(scope="module")
+def model(tiny):
+    from long_vita_b200.megatron.gpt_vl_model import B200GPTVLModel
+
+    cfg, hf, mc = tiny
+    with oracle_ops():
+        return B200GPTVLModel(cfg, mc)
+
+
+def _oracle_logits(cfg, hf, ids, images, idx, rows):
+    w32 = OM.cast_weights(hf, torch.float32)
+    logits = OM.long_vita_forward(cfg, w32, ids, None if images is None else images.float(), idx)
+    return logits[0][rows]
+
+
+def test_forward_indices_mode_with_logit_mask(tiny, model):
+    cfg, hf, _ = tiny
+    ids, images, idx = _inputs(cfg)
+    s = ids.shape[1]
+    mask = torch.zeros(1, s, dtype=torch.bool)
+    mask[0, [10, 299]] = True
+    with oracle_ops():
+        out = model(ids, torch.arange(s).unsqueeze(0), None, external_inputs={"images": images, "indices": idx},
+                    logit_mask=mask)
+    assert out.shape == (1, 2, cfg.vocab_size)                     # [b, M, vocab]
+    ref = _oracle_logits(cfg, hf, ids, images, idx, [10, 299])
+    assert rel_fro(out[0], ref) < 1.5e-2
+    assert torch.equal(out[0].float().argmax(-1), ref.argmax(-1))
+
+
+def test_pre_len_and_src_tgt_modes_equal_indices_mode(tiny, model):
+    cfg, hf, _ = tiny
+    ids, images, idx = _inputs(cfg)
+    s = ids.shape[1]
+    pos = torch.arange(s).unsqueeze(0)
+    with oracle_ops():
+        a = model(ids, pos, None, external_inputs={"images": images, "indices": idx})
+        b = model(ids, pos, None, external_inputs={"images": images, "pre_len": 7})
+        src = (torch.zeros(256, dtype=torch.long), torch.arange(256))
+        tgt = (torch.zeros(256, dtype=torch.long), torch.arange(7, 7 + 256))
+        c = model(ids, pos, None, external_inputs={"images": images, "src_indices": src, "tgt_indices": tgt})
+        # a partial scatter (what a CP rank owning half of the image's tokens does) must differ
+        d = model(ids, pos, None, external_inputs={"images": images, "src_indices": (src[0][:128], src[1][:128]),
+                                                   "tgt_indices": (tgt[0][:128], tgt[1][:128])})
+    assert a.shape == (1, s, cfg.vocab_size)
+    assert torch.equal(a, b) and torch.equal(a, c)
+    assert not torch.equal(a, d)
+    assert torch.equal(a[0, :7], d[0, :7])                              # causal: rows before the image agree
+
+
+def test_labels_give_per_token_loss_and_inference_params_override(tiny, model):
+    cfg, hf, _ = tiny
+    ids, images, idx = _inputs(cfg)
+    s = ids.shape[1]
+    pos = torch.arange(s).unsqueeze(0)
+    mask = torch.zeros(1, s, dtype=torch.bool)
+    mask[0, 280:] = True
+    labels = torch.randint(0, cfg.vocab_size, (1, s), generator=torch.Generator().manual_seed(9))
+    ip = types.SimpleNamespace(external_inputs={"images": images, "indices": idx}, key_value_memory_dict={},
+                               logit_mask=mask, use_kv_cache=False)
+    with oracle_ops():
+        logits = model(ids, pos, None, inference_params=ip)            # both overrides come from inference_params
+        loss = model(ids, pos, None, labels=labels, external_inputs={"images": images, "indices": idx}, logit_mask=mask)
+    assert logits.shape == (1, 20, cfg.vocab_size)
+    assert loss.shape == (1, 20) and loss.dtype == torch.float32
+    ref = torch.nn.functional.cross_entropy(logits[0].float(), labels[0, 280:], reduction="none")
+    assert torch.allclose(loss[0], ref, rtol=0, atol=0)
+    full = _oracle_logits(cfg, hf, ids, images, idx, slice(280, 300))
+    assert rel_fro(logits[0], full) < 1.5e-2
+
+
+def test_guards(tiny, model):
+    cfg, _, _ = tiny
+    ids = torch.zeros(1, 8, dtype=torch.long)
+    pos = torch.arange(8).unsqueeze(0)
+    with oracle_ops():
+        with pytest.raises(AssertionError):
+            model(ids, pos, None, packed_seq_params=object())
+        with pytest.raises(NotImplementedError):
+            model(ids, pos, None, inference_params=types.SimpleNamespace(key_value_memory_dict={1: 2}))
+        with pytest.raises(AssertionError):
+            model.embedding(ids, pos, {"features": torch.zeros(1, 256, cfg.hidden_size), "bogus": 1})
+
+
+def test_product_path_still_refuses_cpu_tensors(tiny):
+    """Outside the harness the wrappers are the real ones: no silent CPU fallback."""
+    from long_vita_b200 import ops
+
+    with pytest.raises(Exception):
+        ops.rmsnorm(torch.zeros(4, 64, dtype=torch.bfloat16), torch.ones(64, dtype=torch.bfloat16))
+
+
+def test_spec_layer_ungroups_megatron_weights(tiny):
+    """B2 (`--spec` layer): TE state-dict names + Megatron's grouped QKV / cat(gate, up) layouts are
+    re-ordered correctly - the layer equals the oracle decoder layer on the same (HF-layout) weights."""
+    from long_vita_b200.megatron.transformer_layer import B200TransformerLayer
+    from oracle import ops as O
+
+    cfg, hf, mc = tiny
+    mcfg = types.SimpleNamespace(hidden_size=cfg.hidden_size, num_attention_heads=cfg.num_attention_heads,
+                                 num_query_groups=cfg.num_key_value_heads, kv_channels=cfg.head_dim,
+                                 ffn_hidden_size=cfg.intermediate_size, layernorm_epsilon=cfg.rms_norm_eps,
+                                 hidden_dropout=0.0, attention_dropout=0.0, params_dtype=torch.bfloat16)
+    layer = B200TransformerLayer(mcfg, layer_number=1)
+    sd = {k[len("decoder.layers.0."):]: v for k, v in mc.items() if k.startswith("decoder.layers.0.")}
+    missing, unexpected = layer.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    s = 192
+    x = torch.randn(s, 1, cfg.hidden_size, generator=torch.Generator().manual_seed(4)).to(torch.bfloat16)
+    inv = O.rope_inv_freq(cfg.head_dim, cfg.rope_theta)
+    freqs = torch.outer(torch.arange(s).float(), inv)
+    rotary = torch.cat((freqs, freqs), dim=-1).view(s, 1, 1, cfg.head_dim)       # Megatron's `freqs` tensor
+    with oracle_ops():
+        out, ctx = layer(hidden_states=x, attention_mask=None, context=None, context_mask=None, rotary_pos_emb=rotary,
+                         inference_params=None, packed_seq_params=None)
+    assert ctx is None and out.shape == (s, 1, cfg.hidden_size)
+    cos, sin = O.rope_tables(torch.arange(s), inv, torch.float32)
+    ref = OM.decoder_layer(cfg, OM.cast_weights(hf, torch.float32), 0, x[:, 0].float(), cos, sin)
+    assert rel_fro(out[:, 0], ref) < 6e-3, rel_fro(out[:, 0], ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# context-parallel host logic, world_size 2 over gloo
+# ------------------------------------------------------------------------------------------------
+class _GlooCPContext:
+    """Stand-in for cp.CPContext with the same two methods the layer uses: the K/V exchange is a gloo
+    all-gather and the attention is the oracle with this rank's zig-zag query positions."""
+
+    def __init__(self, S, hq, hkv, d):
+        import torch.distributed as dist
+
+        from long_vita_b200 import cp as CP
+
+        self.dist, self.CP = dist, CP
+        self.cp, self.rank = dist.get_world_size(), dist.get_rank()
+        self.S, self.hq, self.hkv, self.d = S, hq, hkv, d
+        self.T = S // self.cp
+        self.buf = torch.empty(self.T, (hq + 2 * hkv) * d, dtype=torch.bfloat16)
+
+    def qkv_buffer(self):
+        return self.buf
+
+    def attention(self, out=None, scale=None):
+        from oracle import ops as O
+
+        hq, hkv, d, T = self.hq, self.hkv, self.d, self.T
+        q = self.buf[:, : hq * d].view(T, hq, d)
+        kv = self.buf[:, hq * d :].contiguous()
+        parts = [torch.empty_like(kv) for _ in range(self.cp)]
+        self.dist.all_gather(parts, kv)
+        full = torch.empty(self.S, 2 * hkv * d, dtype=torch.bfloat16)
+        for r in range(self.cp):
+            full[self.CP.zigzag_index(self.S, self.cp, r)] = parts[r]
+        k = full[:, : hkv * d].view(self.S, hkv, d)
+        v = full[:, hkv * d :].view(self.S, hkv, d)
+        o, _ = O.attention(q[None], k[None], v[None], causal=True, scale=scale,
+                           q_pos=self.CP.zigzag_index(self.S, self.cp, self.rank), kv_pos=torch.arange(self.S))
+        return o[0].to(torch.bfloat16).reshape(T, hq * d)
+
+
+def _cp_worker(rank, world, port, tmp):
+    import os
+
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from long_vita_b200 import cp as CP
+        from long_vita_b200.megatron.gpt_vl_model import B200GPTVLModel
+        from long_vita_b200.synthetic import build_prompt
+
+        torch.set_num_threads(2)
+        cfg = LongVITAConfig.tiny(layers=2, vit_layers=1)
+        hf = synthetic_state_dict(cfg, seed=77, dtype=torch.bfloat16, perturb=True)
+        mc = ck.hf_to_mcore(hf, cfg)
+        ids, idx = build_prompt(cfg, 2, n_text=20, pad_multiple=2 * world * 128)
+        S = ids.shape[1]
+        images = torch.randn(2, 3, 448, 448, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+        sh = CP.shard_prompt(ids, idx, world, rank, cfg.visual.tokens_per_image)
+        with oracle_ops():
+            model = B200GPTVLModel(cfg, mc, cp=_GlooCPContext(S, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim))
+            tpi = cfg.visual.tokens_per_image
+            ext = {"images": images[sh.image_sel],
+                   "src_indices": (sh.src_idx // tpi, sh.src_idx % tpi),
+                   "tgt_indices": (torch.zeros_like(sh.dst_idx), sh.dst_idx)}
+            local = model(sh.input_ids, sh.position_ids.unsqueeze(0), None, external_inputs=ext)     # [1, T, vocab]
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local)
+        if rank == 0:
+            full = torch.cat(parts, dim=1)[:, CP.zigzag_unpermute_index(S, world)]
+            torch.save(full, tmp)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_forward_equals_unsharded(tiny, model, tmp_path):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    from long_vita_b200.synthetic import build_prompt
+
+    cfg, hf, _ = tiny
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "sharded.pt")
+    mp.spawn(_cp_worker, args=(2, port, out), nprocs=2, join=True)
+    sharded = torch.load(out)
+    ids, idx = build_prompt(cfg, 2, n_text=20, pad_multiple=2 * 2 * 128)
+    images = torch.randn(2, 3, 448, 448, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+    with oracle_ops():
+        ref = model(ids, torch.arange(ids.shape[1]).unsqueeze(0), None, external_inputs={"images": images, "indices": idx})
+    assert sharded.shape == ref.shape
+    # identical operator sequence per token; only the attention's reduction order differs
+    assert rel_fro(sharded, ref) < 2e-3, rel_fro(sharded, ref)
+    assert (sharded[0].float().argmax(-1) == ref[0].float().argmax(-1)).float().mean() > 0.995
