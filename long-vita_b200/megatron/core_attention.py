@@ -18,8 +18,9 @@ registered after `import long_vita_megatron.megatron_adaptor` (megatron_adaptor.
 
 Megatron-core is NOT importable in the build container (un-vendored submodule), so
 nothing here imports it: the mask type is duck-typed by name and process-group lookups go through
-`parallel_state` only when context parallelism is on.  tests/test_megatron_surface.py drives these
-objects with a stub that reproduces the ModuleSpec / build_module calling convention.
+`parallel_state` only when context parallelism is on.  tests/test_gpu_surfaces.py (kernels) and
+tests/test_surfaces_host.py (host logic, CPU) drive these objects with a stub that reproduces the
+ModuleSpec / build_module calling convention.
 """
 from __future__ import annotations
 
