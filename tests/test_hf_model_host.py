@@ -1,0 +1,79 @@
+"""CPU tests of the host logic of the HF surface: `LongVITAForCausalLM.forward`
+argument handling - image scatter, `num_logits_to_keep`, `inputs_embeds`, explicit `position_ids`,
+`labels` -> shifted loss, `output_hidden_states`, tuple return, guards - with the operator wrappers
+replaced by the CPU oracle (tests/hostlogic.py).  Kernel parity of the same model: tests/test_gpu_model.py."""
+import pytest
+import torch
+
+from long_vita_b200.config import LongVITAConfig
+from long_vita_b200.hf.modeling import LongVITAForCausalLM
+from long_vita_b200.weights import synthetic_state_dict
+from oracle import model as OM
+from tests.hostlogic import oracle_ops
+from tests.util import rel_fro
+
+
+@pytest.fixture(scope="module")
+def setup():
+    cfg = LongVITAConfig.tiny(layers=2, vit_layers=1)
+    w = synthetic_state_dict(cfg, seed=31, dtype=torch.bfloat16, perturb=True)
+    return cfg, w, LongVITAForCausalLM(cfg, w), OM.cast_weights(w, torch.float32)
+
+
+def _inputs(cfg, s=290, seed=2):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, cfg.vocab_size, (1, s), generator=g)
+    images = torch.randn(1, 3, 448, 448, generator=g).to(torch.bfloat16)
+    idx_s = torch.arange(11, 11 + 256).unsqueeze(0)
+    return ids, images, torch.stack([torch.zeros_like(idx_s), idx_s])
+
+
+def test_forward_with_images_keeps_last_rows_and_hidden_states(setup):
+    cfg, w, model, w32 = setup
+    ids, images, idx = _inputs(cfg)
+    with oracle_ops():
+        out = model(input_ids=ids, images=images, image_indices=idx, num_logits_to_keep=3, output_hidden_states=True)
+        tup = model(input_ids=ids, images=images, image_indices=idx, num_logits_to_keep=3, return_dict=False)
+    logits, hidden, h_final = OM.long_vita_forward(cfg, w32, ids, images.float(), idx, num_logits_to_keep=3, return_hidden=True)
+    assert out.logits.shape == (1, 3, cfg.vocab_size) and out.loss is None and out.past_key_values is None
+    assert rel_fro(out.logits[0], logits[0]) < 1.5e-2
+    assert len(out.hidden_states) == cfg.num_hidden_layers + 1
+    for hg, hr in zip(out.hidden_states[:-1], hidden):
+        assert rel_fro(hg[0], hr) < 1e-2
+    assert rel_fro(out.hidden_states[-1][0], h_final) < 1e-2           # the last entry is the normed state
+    assert isinstance(tup, tuple) and torch.equal(tup[0], out.logits)
+
+
+def test_inputs_embeds_position_ids_and_labels(setup):
+    cfg, w, model, w32 = setup
+    ids, _, _ = _inputs(cfg, s=96)
+    labels = ids.clone()
+    labels[0, :10] = -100
+    with oracle_ops():
+        a = model(input_ids=ids, labels=labels)
+        emb = w["model.embed_tokens.weight"][ids[0]].unsqueeze(0)
+        b = model(inputs_embeds=emb)
+        shifted = model(input_ids=ids, position_ids=(torch.arange(96) + 5).unsqueeze(0))
+    assert torch.equal(a.logits, b.logits)
+    ref = OM.long_vita_forward(cfg, w32, ids)
+    assert rel_fro(a.logits[0], ref[0]) < 1.5e-2
+    want = torch.nn.functional.cross_entropy(a.logits[0, :-1].float(), labels[0, 1:], ignore_index=-100)
+    assert torch.allclose(a.loss, want)
+    ref_shift = OM.long_vita_forward(cfg, w32, ids, position_ids=(torch.arange(96) + 5).unsqueeze(0))
+    assert rel_fro(shifted.logits[0], ref_shift[0]) < 1.5e-2
+    assert not torch.equal(shifted.logits, a.logits)                   # RoPE saw the explicit positions
+
+
+def test_guards_raise_before_any_kernel_call(setup):
+    cfg, w, model, _ = setup
+    ids = torch.zeros(1, 8, dtype=torch.long)
+    with pytest.raises(ValueError):
+        model(input_ids=None)
+    with pytest.raises(ValueError):
+        model(input_ids=ids, inputs_embeds=torch.zeros(1, 8, cfg.hidden_size))
+    for kw in ({"use_cache": True}, {"output_attentions": True}, {"past_key_values": [1]},
+               {"attention_mask": torch.tensor([[1, 1, 1, 1, 1, 1, 0, 0]])}):
+        with pytest.raises(NotImplementedError):
+            model(input_ids=ids, **kw)
+    with pytest.raises(NotImplementedError):
+        model(input_ids=torch.zeros(2, 8, dtype=torch.long))
