@@ -405,6 +405,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     n_out = N // 2 if act == "swiglu" else N      # fused SwiGLU: weight rows interleaved (gate_i, up_i)
     if out is None:
         out = torch.empty((M, n_out), dtype=torch.bfloat16, device=x.device)
+    if M == 0:      # e.g. a context-parallel rank that owns no answer token (empty logit mask)
+        return out.view(*x.shape[:-1], n_out)
     ev0 = _TIMER.start() if _TIMER is not None else None
     _lib.check(
         _lib.lib().lv_gemm_bias_act(x2.data_ptr(), weight.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, x2.stride(0),
@@ -433,7 +435,7 @@ def masked_linear(h: torch.Tensor, weight: torch.Tensor, logit_mask: torch.Tenso
         raise NotImplementedError("masked_linear: micro-batch 1")
     idx = logit_mask.reshape(-1).nonzero().view(-1)
     sel = row_gather(h.reshape(s, c), idx)
-    return linear(sel, weight, bias).view(idx.numel(), 1, -1)
+    return linear(sel, weight, bias).view(idx.numel(), 1, weight.shape[0])
 
 
 def masked_linear_dgrad(grad_out: torch.Tensor, weight: torch.Tensor, logit_mask: torch.Tensor):

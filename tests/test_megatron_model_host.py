@@ -294,3 +294,12 @@ def test_two_rank_sharded_forward_equals_unsharded(tiny, model, tmp_path):
     # identical operator sequence per token; only the attention's reduction order differs
     assert rel_fro(sharded, ref) < 2e-3, rel_fro(sharded, ref)
     assert (sharded[0].float().argmax(-1) == ref[0].float().argmax(-1)).float().mean() > 0.995
+
+
+def test_masked_lm_head_with_an_empty_mask():
+    """A context-parallel rank may own no answer token: the masked head then returns [0, b, vocab]."""
+    h = torch.randn(16, 1, 64).to(torch.bfloat16)
+    w = torch.randn(96, 64).to(torch.bfloat16)
+    with oracle_ops() as ops:
+        out = ops.masked_linear(h, w, torch.zeros(1, 16, dtype=torch.bool))
+    assert out.shape == (0, 1, 96)
