@@ -12,10 +12,13 @@ Qwen2Attention / Qwen2MLP / Qwen2RMSNorm / apply_rotary_pos_emb (un-vendored thi
 `transformers>=4.48.3` per requirements.txt:13; the reference file itself no longer imports under
 the installed transformers 5.5.0 - SURVEY.md 8c).
 
-Pinning: tests/test_oracle_pinning.py checks `decoder_layer` against the installed
-transformers.Qwen2DecoderLayer on identical weights, and `vit_forward` / `projector_forward`
-against golden outputs produced by the reference's own InternVisionModel / ResamplerProjector
-(tests/golden/make_golden.py, run in the build container where /root/reference is mounted).
+Pinning: tests/test_oracle_pinning.py checks `long_vita_forward` (every decoder layer's input, the final
+normed state and the logits) against outputs of the reference's OWN `LongVITAForCausalLM.forward`, executed
+from /root/reference in the build container (oracle/ref_loader.py: three API shims for the installed
+transformers 5.5, none touching arithmetic) and committed as tests/golden/ref_long_vita_tiny.pt - agreement
+5e-7 relative in fp32; `vit_forward` / `projector_forward` against golden outputs of the reference's own
+InternVisionModel / ResamplerProjector; and `decoder_layer` against the installed
+transformers.Qwen2DecoderLayer on identical weights (tests/golden/make_golden.py generates the fixtures).
 
 Every function takes a flat state dict with the reference's HF parameter names and computes in
 the dtype of its inputs (fp32 for the accumulating oracle, bf16 to reproduce the eager rounding

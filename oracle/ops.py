@@ -11,10 +11,14 @@ un-vendored third-party package the docstring names it:
   * Megatron-LM core_r0.7.0 @ 5f4c9ac9 and TransformerEngine - the mcore twins of the same ops.
 
 PARITY PINNING: the reference repository ships no tests, golden vectors or fixtures (SURVEY.md
-section 4), so these restatements are pinned against the reference's own importable modules
-(InternViT + ResamplerProjector, see oracle/ref_loader.py and tests/golden/make_golden.py) and,
-for the un-vendored pieces, against the installed third-party implementations the reference calls
-(transformers' Qwen2 modules) - see tests/test_oracle_pinning.py.
+section 4), so these restatements are pinned against OUTPUTS OF THE REFERENCE ITSELF RUN HERE: its
+whole `LongVITAForCausalLM.forward`, and InternViT + ResamplerProjector on their own, executed from
+/root/reference (oracle/ref_loader.py, tests/golden/make_golden.py -> tests/golden/*.pt) and, for the
+un-vendored pieces, against the installed third-party implementations the reference calls
+(transformers' Qwen2 modules) - see tests/test_oracle_pinning.py.  Not pinned by reference outputs: the
+flash-attn / TransformerEngine kernels (CUDA-only, un-vendored) - attention is pinned by its
+definition and a live flash-attn 2.8 comparator on the GPU box - and the Megatron composition (Megatron is
+an empty submodule), which shares every operator with the HF path.
 """
 from __future__ import annotations
 

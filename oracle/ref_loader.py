@@ -1,5 +1,5 @@
-"""Import the reference's own HF vision modules (InternVisionModel, ResamplerProjector,
-pixel_shuffle) from /root/reference WITHOUT copying them - only possible in the build container
+"""Import the reference's own HF modules (InternVisionModel, ResamplerProjector, pixel_shuffle, and - through
+`load_long_vita()` - the whole LongVITAForCausalLM) from /root/reference WITHOUT copying them - only possible in the build container
 where the reference is mounted; used by tests/golden/make_golden.py to generate golden vectors
 and by tests/test_oracle_pinning.py when the mount exists.
 
@@ -82,5 +82,80 @@ def load():
         InternVisionModel=vit.InternVisionModel,
         ResamplerProjector=proj.ResamplerProjector,
         pixel_shuffle=proj.pixel_shuffle,
+        _imp=imp,
     )
     return ns
+
+
+def load_long_vita():
+    """The reference's whole-model classes `LongVITAConfig`, `LongVITAModel`, `LongVITAForCausalLM`
+    (modeling_long_vita.py, executed from /root/reference where it lies - nothing is copied).
+
+    The file targets transformers >= 4.48.3 (requirements.txt:13) and no longer runs as-is under the
+    installed 5.5.0.  Three API shims, none of which touches the reference's arithmetic:
+      1. `transformers.utils.LossKwargs` (imported at :24, used only as a typing base at :224) was
+         removed -> an empty TypedDict is put back;
+      2. `Qwen2Model._update_causal_mask` (called at :162) was removed -> replaced by the explicit
+         additive causal mask [1, 1, s, s] it used to return for eager / sdpa attention;
+      3. `Qwen2DecoderLayer.forward` now returns a tensor, the reference indexes `layer_outputs[0]`
+         (:204) as under 4.48 -> each layer's forward is wrapped to return a 1-tuple
+         (`wrap_decoder_layers(model)`, call it after constructing the model).
+    With these the unmodified reference forward runs on CPU (`attn_implementation="eager"`,
+    `use_flash_attn=False` in the visual config)."""
+    import torch
+    import transformers.utils as TU
+    from typing import TypedDict
+
+    ns = load()
+    if not hasattr(TU, "LossKwargs"):
+        TU.LossKwargs = TypedDict("LossKwargs", {}, total=False)
+    cfg = ns._imp("configuration_long_vita")
+    mod = ns._imp("modeling_long_vita")
+
+    def _update_causal_mask(self, attention_mask, input_tensor, cache_position, past_key_values, output_attentions=False):
+        s = input_tensor.shape[1]
+        m = torch.full((s, s), torch.finfo(input_tensor.dtype).min, dtype=input_tensor.dtype, device=input_tensor.device)
+        return torch.triu(m, diagonal=1)[None, None]
+
+    if not hasattr(mod.LongVITAModel, "_update_causal_mask"):
+        mod.LongVITAModel._update_causal_mask = _update_causal_mask
+
+    def wrap_decoder_layers(model):
+        for layer in model.model.layers:
+            orig = layer.forward
+
+            def fwd(*a, _orig=orig, **k):
+                out = _orig(*a, **k)
+                return out if isinstance(out, tuple) else (out,)
+
+            layer.forward = fwd
+        return model
+
+    ns.LongVITAConfig = cfg.LongVITAConfig
+    ns.LongVITAModel = mod.LongVITAModel
+    ns.LongVITAForCausalLM = mod.LongVITAForCausalLM
+    ns.wrap_decoder_layers = wrap_decoder_layers
+    return ns
+
+
+def build_reference_long_vita(cfg, state_dict):
+    """Instantiate the reference `LongVITAForCausalLM` for our `LongVITAConfig` geometry `cfg` and load
+    `state_dict` (HF names - the names `weights.synthetic_state_dict` produces are the reference's)."""
+    ns = load_long_vita()
+    v = cfg.visual
+    visual = dict(attention_dropout=0.0, drop_path_rate=0.0, dropout=0.0, hidden_act="gelu", hidden_size=v.hidden_size,
+                  image_size=v.image_size, initializer_factor=1.0, initializer_range=0.02,
+                  intermediate_size=v.intermediate_size, layer_norm_eps=v.layer_norm_eps, norm_type="layer_norm",
+                  num_attention_heads=v.num_attention_heads, num_channels=3, num_hidden_layers=v.num_hidden_layers,
+                  patch_size=v.patch_size, qk_normalization=False, qkv_bias=True, use_flash_attn=False)
+    rc = ns.LongVITAConfig(visual=visual, attention_dropout=0.0, hidden_act="silu", hidden_size=cfg.hidden_size,
+                           initializer_range=cfg.initializer_range, intermediate_size=cfg.intermediate_size,
+                           max_position_embeddings=1 << 20, num_attention_heads=cfg.num_attention_heads,
+                           num_hidden_layers=cfg.num_hidden_layers, num_key_value_heads=cfg.num_key_value_heads,
+                           rms_norm_eps=cfg.rms_norm_eps, rope_theta=cfg.rope_theta, tie_word_embeddings=False,
+                           use_cache=False, use_sliding_window=False, vocab_size=cfg.vocab_size,
+                           attn_implementation="eager")
+    model = ns.LongVITAForCausalLM(rc).eval()
+    missing, unexpected = model.load_state_dict(state_dict, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    return ns.wrap_decoder_layers(model)

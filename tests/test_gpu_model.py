@@ -132,3 +132,30 @@ def test_siglip_tower_matches_oracle(lib_built):
     ref = OM.siglip_forward(cfg, OM.cast_weights(w, torch.float32), images.float())
     assert out.shape == (2, 1024, C)
     assert rel_fro(out, ref) < 6e-3, rel_fro(out, ref)
+
+
+def test_whole_forward_matches_the_references_own_forward(lib_built):
+    """GPU model against the committed outputs of the reference's own LongVITAForCausalLM.forward run on CPU in
+    fp32 (tests/golden/ref_long_vita_tiny.pt, generated by tests/golden/make_golden.py from /root/reference)."""
+    import os
+    import sys
+
+    from long_vita_b200.hf import modeling
+
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold_dir)
+    from make_golden import long_vita_inputs
+
+    gold = torch.load(os.path.join(gold_dir, "ref_long_vita_tiny.pt"))
+    cfg = LongVITAConfig.tiny(layers=2, vit_layers=1)
+    w = synthetic_state_dict(cfg, seed=gold["seed"], dtype=torch.float32, perturb=True)
+    ids, images, idx = long_vita_inputs(cfg, gold["seed"])
+    model = modeling.LongVITAForCausalLM(cfg, {k: v.to(torch.bfloat16).cuda() for k, v in w.items()})
+    out = model(input_ids=ids.cuda(), images=images.to(torch.bfloat16).cuda(), image_indices=idx.cuda(),
+                num_logits_to_keep=8, output_hidden_states=True)
+    # the fixture is fp32 with fp32 weights; bf16 weights + activations alone give ~6.6e-3 (CPU emulation)
+    assert rel_fro(out.logits[0], gold["logits_last8"]) < 2e-2, rel_fro(out.logits[0], gold["logits_last8"])
+    assert torch.equal(out.logits[0].float().argmax(-1).cpu(), gold["logits_last8"].argmax(-1))
+    rows = gold["rows"]
+    for li in range(cfg.num_hidden_layers + 1):
+        assert rel_fro(out.hidden_states[li][0].cpu()[rows], gold["hidden_rows"][li]) < 1.5e-2, li

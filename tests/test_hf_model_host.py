@@ -77,3 +77,29 @@ def test_guards_raise_before_any_kernel_call(setup):
             model(input_ids=ids, **kw)
     with pytest.raises(NotImplementedError):
         model(input_ids=torch.zeros(2, 8, dtype=torch.long))
+
+
+def test_product_composition_against_the_references_own_forward():
+    """The product's HF-surface model (host logic; kernels replaced by the oracle) against the committed outputs
+    of the reference's own LongVITAForCausalLM.forward (tests/golden/ref_long_vita_tiny.pt)."""
+    import os
+    import sys
+
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold_dir)
+    from make_golden import long_vita_inputs
+
+    gold = torch.load(os.path.join(gold_dir, "ref_long_vita_tiny.pt"))
+    cfg = LongVITAConfig.tiny(layers=2, vit_layers=1)
+    w = synthetic_state_dict(cfg, seed=gold["seed"], dtype=torch.float32, perturb=True)
+    ids, images, idx = long_vita_inputs(cfg, gold["seed"])
+    model = LongVITAForCausalLM(cfg, {k: v.to(torch.bfloat16) for k, v in w.items()})
+    with oracle_ops():
+        out = model(input_ids=ids, images=images.to(torch.bfloat16), image_indices=idx, num_logits_to_keep=8,
+                    output_hidden_states=True)
+    # the fixture is fp32 with fp32 weights; bf16 weights + activations alone give ~6.6e-3
+    assert rel_fro(out.logits[0], gold["logits_last8"]) < 2e-2
+    assert torch.equal(out.logits[0].float().argmax(-1), gold["logits_last8"].argmax(-1))
+    rows = gold["rows"]
+    for li in range(cfg.num_hidden_layers + 1):
+        assert rel_fro(out.hidden_states[li][0][rows], gold["hidden_rows"][li]) < 1.5e-2, li

@@ -1,9 +1,10 @@
 """Pin the CPU oracle (tests are CPU-only).
 
 The reference ships no tests or golden vectors, so the oracle is pinned against
-  (1) golden outputs generated from the reference's OWN InternVisionModel / ResamplerProjector /
-      pixel_shuffle (tests/golden/make_golden.py; regenerated and compared live when
-      /root/reference is mounted),
+  (1) golden outputs generated from the reference's OWN code run in the build container
+      (tests/golden/make_golden.py; regenerated and compared live when /root/reference is mounted):
+      InternVisionModel / ResamplerProjector / pixel_shuffle, and the WHOLE LongVITAForCausalLM.forward
+      (vision tower -> projector -> embedding scatter -> Qwen2 decoder -> norm -> lm_head),
   (2) the installed third-party modules whose arithmetic the reference delegates to
       (transformers Qwen2DecoderLayer / Qwen2RMSNorm / rotary embedding),
   (3) internal identities: the zig-zag ring schedule equals full causal attention, zig-zag
@@ -54,6 +55,47 @@ def test_live_reference_modules_agree_with_golden_files():
     ref = ref_loader.load()
     gold = torch.load(os.path.join(GOLD, "ref_pixel_shuffle.pt"))
     assert torch.equal(ref.pixel_shuffle(gold["x"], 0.5), gold["y"])
+
+
+def _sha(t):
+    return hashlib.sha256(t.contiguous().view(torch.int32).numpy().tobytes()).hexdigest()
+
+
+def _long_vita_golden():
+    from make_golden import LV_SEED, long_vita_inputs
+
+    gold = torch.load(os.path.join(GOLD, "ref_long_vita_tiny.pt"))
+    assert gold["seed"] == LV_SEED
+    cfg = LongVITAConfig.tiny(layers=2, vit_layers=1)
+    w = synthetic_state_dict(cfg, seed=gold["seed"], dtype=torch.float32, perturb=True)
+    ids, images, idx = long_vita_inputs(cfg, gold["seed"])
+    # the fixture was produced from these very tensors (guards against RNG drift between torch versions)
+    assert _sha(images) == gold["images_sha256"] and _sha(w["model.embed_tokens.weight"]) == gold["embed_sha256"]
+    return gold, cfg, w, ids, images, idx
+
+
+def test_whole_model_oracle_matches_the_references_own_forward():
+    """oracle.model.long_vita_forward against outputs of the reference's LongVITAForCausalLM.forward itself
+    (modeling_long_vita.py, run from /root/reference by tests/golden/make_golden.py): every decoder layer's
+    input, the final normed state and the logits, fp32."""
+    gold, cfg, w, ids, images, idx = _long_vita_golden()
+    logits, hidden, h_final = OM.long_vita_forward(cfg, w, ids, images, idx, num_logits_to_keep=8, return_hidden=True)
+    rows = gold["rows"]
+    ref_h = gold["hidden_rows"]                       # [layers + 1 (inputs of each layer ... final norm), 16, H]
+    for li in range(cfg.num_hidden_layers):
+        assert torch.allclose(hidden[li][rows], ref_h[li], rtol=2e-4, atol=2e-4), (li, float((hidden[li][rows] - ref_h[li]).abs().max()))
+    assert torch.allclose(h_final[rows], ref_h[-1], rtol=2e-4, atol=2e-4)
+    assert torch.allclose(logits[0], gold["logits_last8"], rtol=2e-4, atol=2e-4), float((logits[0] - gold["logits_last8"]).abs().max())
+    assert float((logits[0] - gold["logits_last8"]).norm() / gold["logits_last8"].norm()) < 1e-5
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted (GPU box)")
+def test_live_reference_forward_reproduces_the_whole_model_golden():
+    gold, cfg, w, ids, images, idx = _long_vita_golden()
+    model = ref_loader.build_reference_long_vita(cfg, w)
+    with torch.no_grad():
+        out = model(input_ids=ids, images=images, image_indices=idx, num_logits_to_keep=8)
+    assert torch.allclose(out.logits[0], gold["logits_last8"], rtol=1e-5, atol=1e-5)
 
 
 def _hf_qwen2_layer(cfg, w, i=0):
