@@ -159,3 +159,67 @@ def build_reference_long_vita(cfg, state_dict):
     missing, unexpected = model.load_state_dict(state_dict, strict=False)
     assert not missing and not unexpected, (missing, unexpected)
     return ns.wrap_decoder_layers(model)
+
+
+# ------------------------------------------------------------------------------------------------
+# Megatron-side helpers of the reference that are plain torch once their imports are satisfied
+# ------------------------------------------------------------------------------------------------
+def load_megatron_training_utils(cp_size: int, cp_rank: int, seq_length: int):
+    """The reference's `long_vita_megatron/training/utils.py` (get_batch_on_this_cp_rank :252-343,
+    index_of_a_in_b :347-350), executed from /root/reference.  Megatron-LM is an empty submodule there, so the
+    module's imports are satisfied by empty stand-ins (`megatron.training.get_args` returns a namespace with
+    the three fields the function reads, `mpu.get_context_parallel_rank` returns `cp_rank`).  Returns
+    (module, cpu_placement) where `cpu_placement()` is a context manager under which the function's
+    `device='cuda'` / `.cuda()` / `pin_memory=True` placements resolve to the CPU - placement only, no
+    arithmetic is touched."""
+    import contextlib
+    import importlib.machinery
+
+    import torch
+
+    if not os.path.isdir(REF_ROOT):
+        raise RuntimeError("/root/reference is not mounted on this machine")
+    args = types.SimpleNamespace(reset_position_ids=False, context_parallel_size=cp_size, seq_length=seq_length)
+
+    def mk(name, **attrs):
+        m = types.ModuleType(name)
+        m.__spec__ = importlib.machinery.ModuleSpec(name, loader=None)
+        m.__path__ = []
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    mpu = mk("megatron.core.mpu", get_context_parallel_rank=lambda: cp_rank,
+             get_context_parallel_world_size=lambda: cp_size)
+    mk("megatron")
+    mk("megatron.training", get_args=lambda: args, get_adlr_autoresume=lambda: None)
+    mk("megatron.core", DistributedDataParallel=type("DDP", (), {}), mpu=mpu)
+    mk("megatron.core.tensor_parallel", param_is_not_tensor_parallel_duplicate=lambda p: True)
+    mk("megatron.legacy")
+    mk("megatron.legacy.model", Float16Module=type("Float16Module", (), {}))
+    mk("megatron.legacy.model.module", param_is_not_shared=lambda p: True)
+    path = os.path.join(REF_ROOT, "long_vita_megatron", "training", "utils.py")
+    spec = importlib.util.spec_from_file_location("lv_ref_megatron_training_utils", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    @contextlib.contextmanager
+    def cpu_placement():
+        o_arange, o_tensor, o_cuda = torch.arange, torch.tensor, torch.Tensor.cuda
+
+        def strip(kw):
+            if kw.get("device") == "cuda":
+                kw.pop("device")
+            kw.pop("pin_memory", None)
+            return kw
+
+        torch.arange = lambda *a, **k: o_arange(*a, **strip(k))
+        torch.tensor = lambda *a, **k: o_tensor(*a, **strip(k))
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        try:
+            yield
+        finally:
+            torch.arange, torch.tensor, torch.Tensor.cuda = o_arange, o_tensor, o_cuda
+
+    return mod, cpu_placement

@@ -88,3 +88,37 @@ def test_two_rank_gloo_shard_gather_roundtrip():
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port), nprocs=2, join=True)   # a failed assert in a worker re-raises here
+
+
+def test_shard_prompt_equals_the_references_own_get_batch_on_this_cp_rank():
+    """cp.shard_prompt against committed outputs of the reference's own function (training/utils.py:252-343,
+    executed from /root/reference by tests/golden/make_golden.py with Megatron's imports stubbed and device
+    placement redirected to the CPU): token and position slices, kept images, (src, tgt) scatter indices -
+    bit-exact for cp in {2, 4} and every rank."""
+    import sys
+
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold_dir)
+    from make_golden import cp_golden_prompt
+
+    gold = torch.load(os.path.join(gold_dir, "ref_cp_shards.pt"))
+    ids, idx = cp_golden_prompt()
+    assert ids.shape[1] == gold["S"] and idx.shape[1] == gold["n_frames"]
+    checked = 0
+    for (cp, r), b in gold["shards"].items():
+        sh = CP.shard_prompt(ids, idx, cp, r, 256)
+        assert torch.equal(sh.input_ids, b["tokens"])
+        assert torch.equal(sh.position_ids, b["position_ids"][0])
+        assert "external_indices" not in b                       # consumed by the reference function
+        if "external_src_indices" in b:
+            src_b, src_s = b["external_src_indices"]
+            tgt_b, tgt_s = b["external_tgt_indices"]
+            assert torch.equal(sh.image_sel, b["external_images"].view(-1))
+            assert torch.equal(sh.src_idx, src_b * 256 + src_s)
+            assert not tgt_b.any() and torch.equal(sh.dst_idx, tgt_s)
+            checked += 1
+        else:                                                    # no image token on this rank
+            assert sh.image_sel.numel() == 0 and sh.dst_idx.numel() == 0
+    assert checked >= 5
+    a, b, want = gold["index_of_a_in_b"]
+    assert torch.equal(O.index_of_a_in_b(a, b), want)

@@ -98,6 +98,26 @@ def test_live_reference_forward_reproduces_the_whole_model_golden():
     assert torch.allclose(out.logits[0], gold["logits_last8"], rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted (GPU box)")
+def test_live_reference_cp_function_reproduces_the_shard_golden():
+    from make_golden import cp_golden_prompt
+
+    gold = torch.load(os.path.join(GOLD, "ref_cp_shards.pt"))
+    ids, idx = cp_golden_prompt()
+    S = ids.shape[1]
+    for (cp, r), want in list(gold["shards"].items())[:3]:
+        mod, cpu_placement = ref_loader.load_megatron_training_utils(cp, r, S)
+        batch = {"tokens": ids.clone(), "position_ids": torch.arange(S).unsqueeze(0),
+                 "external_images": torch.arange(idx.shape[1]).view(-1, 1).clone(), "external_indices": idx.clone(),
+                 "attention_mask": None}
+        with cpu_placement():
+            b = mod.get_batch_on_this_cp_rank(batch)
+        assert set(b) == set(want)
+        for k, v in want.items():
+            assert (v is None and b[k] is None) or torch.equal(b[k], v), (cp, r, k)
+    assert torch.arange(3, device="cpu").device.type == "cpu" and torch.tensor([1]).sum() == 1   # patches were undone
+
+
 def _hf_qwen2_layer(cfg, w, i=0):
     from transformers import Qwen2Config
     from transformers.models.qwen2 import modeling_qwen2 as Q
