@@ -214,12 +214,49 @@ def load_megatron_training_utils(cp_size: int, cp_rank: int, seq_length: int):
             kw.pop("pin_memory", None)
             return kw
 
-        torch.arange = lambda *a, **k: o_arange(*a, **strip(k))
-        torch.tensor = lambda *a, **k: o_tensor(*a, **strip(k))
+        def fix(kw):
+            kw = strip(kw)
+            if isinstance(kw.get("device"), int):        # torch.cuda.current_device() used as a device
+                kw.pop("device")
+            return kw
+
+        o_cur = torch.cuda.current_device
+        torch.arange = lambda *a, **k: o_arange(*a, **fix(k))
+        torch.tensor = lambda *a, **k: o_tensor(*a, **fix(k))
         torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.cuda.current_device = lambda: 0
         try:
             yield
         finally:
             torch.arange, torch.tensor, torch.Tensor.cuda = o_arange, o_tensor, o_cuda
+            torch.cuda.current_device = o_cur
 
+    return mod, cpu_placement
+
+
+def load_megatron_rope(cp_size: int, cp_rank: int):
+    """The reference's `long_vita_megatron/core/models/common/embeddings/rotary_pos_embedding.py`
+    (RotaryEmbedding :50-122, get_pos_emb_on_this_cp_rank :36-47, apply_rotary_pos_emb_bshd :181-204), executed
+    from /root/reference with `megatron.core.parallel_state` and `long_vita_megatron.training.utils` satisfied by
+    the stand-ins of `load_megatron_training_utils`.  Returns (module, cpu_placement)."""
+    utils_mod, cpu_placement = load_megatron_training_utils(cp_size, cp_rank, 0)
+    import importlib.machinery
+
+    ps = types.ModuleType("megatron.core.parallel_state")
+    ps.__spec__ = importlib.machinery.ModuleSpec("megatron.core.parallel_state", loader=None)
+    ps.get_context_parallel_world_size = lambda: cp_size
+    ps.get_context_parallel_rank = lambda: cp_rank
+    sys.modules["megatron.core.parallel_state"] = ps
+    sys.modules["megatron.core"].parallel_state = ps
+    for name in ("long_vita_megatron", "long_vita_megatron.training"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__spec__ = importlib.machinery.ModuleSpec(name, loader=None)
+            m.__path__ = []
+            sys.modules[name] = m
+    sys.modules["long_vita_megatron.training.utils"] = utils_mod
+    path = os.path.join(REF_ROOT, "long_vita_megatron", "core", "models", "common", "embeddings", "rotary_pos_embedding.py")
+    spec = importlib.util.spec_from_file_location("lv_ref_megatron_rope", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
     return mod, cpu_placement

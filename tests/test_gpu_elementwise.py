@@ -68,6 +68,24 @@ def test_rope_table_and_apply(L):
     assert torch.equal(ok.cpu(), O.rope_apply(k, cos_r, sin_r))
 
 
+def test_rope_kernel_reproduces_the_references_megatron_rope_bit_exactly(L):
+    """lv_rope on the angles' bf16 cos / sin against the committed output of the reference's own
+    apply_rotary_pos_emb_bshd (tests/golden/ref_megatron_rope.pt, generated from /root/reference)."""
+    import os
+    import sys
+
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold_dir)
+    from make_golden import rope_golden_input
+
+    gold = torch.load(os.path.join(gold_dir, "ref_megatron_rope.pt"))
+    t = rope_golden_input()[:, 0]                                   # [S, heads, 128]
+    ang = gold["emb"].view(gold["S"], 128)
+    cos, sin = torch.cos(ang).to(torch.bfloat16), torch.sin(ang).to(torch.bfloat16)     # :200-201
+    out = L.rope(t.cuda(), cos.cuda(), sin.cuda())
+    assert torch.equal(out.cpu(), gold["applied"][:, 0])
+
+
 def test_swiglu(L):
     g = seeded(5)
     gu = randn_bf16((77, 2 * 13824), g, 2.0)

@@ -118,6 +118,28 @@ def test_live_reference_cp_function_reproduces_the_shard_golden():
     assert torch.arange(3, device="cpu").device.type == "cpu" and torch.tensor([1]).sum() == 1   # patches were undone
 
 
+def test_rope_matches_the_references_own_megatron_rope():
+    """oracle rope tables / apply against the reference's Megatron RotaryEmbedding.forward and
+    apply_rotary_pos_emb_bshd (rotary_pos_embedding.py:84-122, 181-204) - bit-exact - and the zig-zag slice of the
+    table under cp = 2 (:36-47) against the table evaluated at cp.zigzag_index positions."""
+    from make_golden import rope_golden_input
+
+    from long_vita_b200 import cp as CP
+
+    gold = torch.load(os.path.join(GOLD, "ref_megatron_rope.pt"))
+    S = gold["S"]
+    inv = O.rope_inv_freq(128, 1e6)
+    freqs = torch.outer(torch.arange(S).float(), inv)
+    emb = torch.cat((freqs, freqs), dim=-1)
+    assert torch.equal(emb, gold["emb"].view(S, 128))
+    t = rope_golden_input()
+    cos, sin = O.rope_tables(torch.arange(S), inv, torch.bfloat16)
+    assert torch.equal(O.rope_apply(t[:, 0], cos, sin), gold["applied"][:, 0])
+    for r in range(2):
+        own = CP.zigzag_index(S, 2, r)
+        assert torch.equal(emb[own], gold[f"emb_cp2_rank{r}"].view(-1, 128))
+
+
 def _hf_qwen2_layer(cfg, w, i=0):
     from transformers import Qwen2Config
     from transformers.models.qwen2 import modeling_qwen2 as Q
