@@ -260,3 +260,42 @@ def load_megatron_rope(cp_size: int, cp_rank: int):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod, cpu_placement
+
+
+def load_megatron_embedding():
+    """The reference's `LanguageModelEmbedding` (core/models/common/embeddings/language_model_embedding.py:13-174:
+    vocabulary gather + the three image-feature merge modes `indices` / `pre_len` / `src_indices`+`tgt_indices`,
+    transpose to [s, b, h]), executed from /root/reference.  Megatron base classes are stand-ins
+    (`MegatronModule` = torch.nn.Module holding `config`; cp world size 1).  Returns the class."""
+    import importlib.machinery
+
+    import torch
+
+    load_megatron_training_utils(1, 0, 0)             # installs the megatron.* stand-in modules
+
+    def mk(name, **attrs):
+        m = sys.modules.get(name)
+        if m is None:
+            m = types.ModuleType(name)
+            m.__spec__ = importlib.machinery.ModuleSpec(name, loader=None)
+            m.__path__ = []
+            sys.modules[name] = m
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        return m
+
+    class MegatronModule(torch.nn.Module):
+        def __init__(self, config=None):
+            super().__init__()
+            self.config = config
+
+    tp = mk("megatron.core.tensor_parallel", VocabParallelEmbedding=None)
+    mk("megatron.core", tensor_parallel=tp)
+    mk("megatron.core.transformer")
+    mk("megatron.core.transformer.module", MegatronModule=MegatronModule)
+    mk("megatron.core.transformer.transformer_config", TransformerConfig=object)
+    path = os.path.join(REF_ROOT, "long_vita_megatron", "core", "models", "common", "embeddings", "language_model_embedding.py")
+    spec = importlib.util.spec_from_file_location("lv_ref_megatron_embedding", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.LanguageModelEmbedding

@@ -303,3 +303,28 @@ def test_masked_lm_head_with_an_empty_mask():
     with oracle_ops() as ops:
         out = ops.masked_linear(h, w, torch.zeros(1, 16, dtype=torch.bool))
     assert out.shape == (0, 1, 96)
+
+
+def test_embedding_modes_equal_the_references_own_embedding(tiny):
+    """B200GPTVLModel.embedding (index translation to lv_embed_scatter's flat src / dst form) against committed
+    outputs of the reference's own LanguageModelEmbedding.forward - bit-exact in all four modes."""
+    import os
+    import sys
+
+    from long_vita_b200.megatron.gpt_vl_model import B200GPTVLModel
+
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold_dir)
+    from make_golden import embedding_golden_inputs
+
+    gold = torch.load(os.path.join(gold_dir, "ref_megatron_embedding.pt"))
+    table, ids, feat, idx = embedding_golden_inputs()
+    m = B200GPTVLModel.__new__(B200GPTVLModel)              # only the embedding path: no decoder weights needed
+    m.word_embeddings = table
+    pos = torch.arange(ids.shape[1]).unsqueeze(0)
+    with oracle_ops():
+        assert torch.equal(m.embedding(ids, pos), gold["none"][:, 0])
+        assert torch.equal(m.embedding(ids, pos, {"features": feat, "indices": idx}), gold["indices"][:, 0])
+        assert torch.equal(m.embedding(ids, pos, {"features": feat[:1], "pre_len": 5}), gold["pre_len"][:, 0])
+        got = m.embedding(ids, pos, {"features": feat, "src_indices": gold["src"], "tgt_indices": gold["tgt"]})
+        assert torch.equal(got, gold["src_tgt"][:, 0])

@@ -140,6 +140,21 @@ def test_rope_matches_the_references_own_megatron_rope():
         assert torch.equal(emb[own], gold[f"emb_cp2_rank{r}"].view(-1, 128))
 
 
+def test_embedding_merge_modes_match_the_references_own_embedding():
+    """oracle.embed_scatter against the reference's LanguageModelEmbedding.forward (language_model_embedding.py
+    :91-174) in its four `external_feature_dict` shapes - bit-exact (index ops)."""
+    from make_golden import embedding_golden_inputs
+
+    gold = torch.load(os.path.join(GOLD, "ref_megatron_embedding.pt"))
+    table, ids, feat, idx = embedding_golden_inputs()
+    s, tpi = ids.shape[1], feat.shape[1]
+    assert torch.equal(O.embed_scatter(ids.view(-1), table), gold["none"][:, 0])                    # [s, b, h] -> [s, h]
+    assert torch.equal(O.embed_scatter(ids.view(-1), table, feat, idx[1].reshape(-1)), gold["indices"][:, 0])
+    assert torch.equal(O.embed_scatter(ids.view(-1), table, feat[:1], 5 + torch.arange(tpi)), gold["pre_len"][:, 0])
+    (src_b, src_s), (tgt_b, tgt_s) = gold["src"], gold["tgt"]
+    assert torch.equal(O.embed_scatter(ids.view(-1), table, feat, tgt_b * s + tgt_s, src_b * tpi + src_s), gold["src_tgt"][:, 0])
+
+
 def _hf_qwen2_layer(cfg, w, i=0):
     from transformers import Qwen2Config
     from transformers.models.qwen2 import modeling_qwen2 as Q
