@@ -299,3 +299,56 @@ def load_megatron_embedding():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.LanguageModelEmbedding
+
+
+def load_megatron_masked_linear():
+    """The reference's `LinearWithGradAccumulationAndAsyncCommunication` (core/tensor_parallel/layers.py:365-534:
+    forward / backward of the linear layer with `logit_mask` - masked_select of the rows before the GEMM,
+    masked_scatter of dX after it, dW = dY^T sel), executed from /root/reference.  The module's Megatron imports
+    are stand-ins; the only one that runs on this path (tp = 1, no sequence parallelism, no fused wgrad) is
+    `megatron.core.utils.prepare_input_tensors_for_wgrad_compute`, restated from Megatron-LM core_r0.7.0
+    (flatten [M, b, *] to 2-D).  Returns the autograd Function class."""
+    import importlib.machinery
+
+    load_megatron_training_utils(1, 0, 0)
+
+    def mk(name, **attrs):
+        m = sys.modules.get(name)
+        if m is None:
+            m = types.ModuleType(name)
+            m.__spec__ = importlib.machinery.ModuleSpec(name, loader=None)
+            m.__path__ = []
+            sys.modules[name] = m
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        return m
+
+    def prepare_input_tensors_for_wgrad_compute(grad_output, all_gathered_input):
+        if grad_output.dim() == 3:
+            grad_output = grad_output.contiguous().view(grad_output.shape[0] * grad_output.shape[1], grad_output.shape[2])
+            all_gathered_input = all_gathered_input.contiguous().view(
+                all_gathered_input.shape[0] * all_gathered_input.shape[1], all_gathered_input.shape[2])
+        return grad_output, all_gathered_input
+
+    none = lambda *a, **k: None   # noqa: E731
+    mk("megatron.core.model_parallel_config", ModelParallelConfig=object)
+    mk("megatron.core.parallel_state", get_global_memory_buffer=none, get_tensor_and_expert_parallel_rank=lambda: 0,
+       get_tensor_and_expert_parallel_world_size=lambda: 1, get_tensor_model_parallel_group=none,
+       get_tensor_model_parallel_rank=lambda: 0, get_tensor_model_parallel_world_size=lambda: 1)
+    mk("megatron.core.dist_checkpointing")
+    mk("megatron.core.dist_checkpointing.mapping", ShardedStateDict=dict)
+    mk("megatron.core.transformer")
+    mk("megatron.core.transformer.utils", make_sharded_tensors_for_checkpoint=none)
+    mk("megatron.core.utils", make_tp_sharded_tensor_for_checkpoint=none,
+       prepare_input_tensors_for_wgrad_compute=prepare_input_tensors_for_wgrad_compute)
+    mk("megatron.core.tensor_parallel.mappings", copy_to_tensor_model_parallel_region=none,
+       gather_from_sequence_parallel_region=none, gather_from_tensor_model_parallel_region=none,
+       reduce_from_tensor_model_parallel_region=none, reduce_scatter_to_sequence_parallel_region=none,
+       scatter_to_tensor_model_parallel_region=none)
+    mk("megatron.core.tensor_parallel.random", get_cuda_rng_tracker=none, get_expert_parallel_rng_tracker_name=none)
+    mk("megatron.core.tensor_parallel.utils", VocabUtility=object, divide=lambda a, b: a // b, split_tensor_along_last_dim=none)
+    path = os.path.join(REF_ROOT, "long_vita_megatron", "core", "tensor_parallel", "layers.py")
+    spec = importlib.util.spec_from_file_location("lv_ref_megatron_layers", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.LinearWithGradAccumulationAndAsyncCommunication

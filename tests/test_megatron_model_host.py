@@ -328,3 +328,24 @@ def test_embedding_modes_equal_the_references_own_embedding(tiny):
         assert torch.equal(m.embedding(ids, pos, {"features": feat[:1], "pre_len": 5}), gold["pre_len"][:, 0])
         got = m.embedding(ids, pos, {"features": feat, "src_indices": gold["src"], "tgt_indices": gold["tgt"]})
         assert torch.equal(got, gold["src_tgt"][:, 0])
+
+
+def test_masked_lm_head_forward_and_dgrad_equal_the_references_own_function():
+    """ops.masked_linear / masked_linear_dgrad (gather -> GEMM, GEMM -> scatter-with-zeros; kernels replaced by the
+    oracle) against committed outputs of the reference's own autograd function (layers.py:365-534)."""
+    import os
+    import sys
+
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold_dir)
+    from make_golden import masked_linear_golden_inputs
+
+    gold = torch.load(os.path.join(gold_dir, "ref_megatron_masked_linear.pt"))
+    h, w, mask, dy = masked_linear_golden_inputs()
+    bf = torch.bfloat16
+    with oracle_ops() as ops:
+        out = ops.masked_linear(h.to(bf), w.to(bf), mask)
+        dx = ops.masked_linear_dgrad(dy.to(bf), w.to(bf), mask)
+    assert out.shape == gold["out"].shape and rel_fro(out, gold["out"]) < 8e-3      # bf16 inputs vs the fp32 fixture
+    assert dx.shape == gold["dx"].shape and rel_fro(dx, gold["dx"]) < 8e-3
+    assert torch.equal(dx[:, 0].float().abs().sum(-1) == 0, gold["dx"][:, 0].abs().sum(-1) == 0)   # same zero rows

@@ -155,6 +155,20 @@ def test_embedding_merge_modes_match_the_references_own_embedding():
     assert torch.equal(O.embed_scatter(ids.view(-1), table, feat, tgt_b * s + tgt_s, src_b * tpi + src_s), gold["src_tgt"][:, 0])
 
 
+def test_masked_linear_matches_the_references_own_autograd_function():
+    """oracle masked_linear_fwd / _bwd against the reference's LinearWithGradAccumulationAndAsyncCommunication with
+    logit_mask (layers.py:365-534): output, dX = masked_scatter(zeros, dY W), dW = dY^T sel (fp32)."""
+    from make_golden import masked_linear_golden_inputs
+
+    gold = torch.load(os.path.join(GOLD, "ref_megatron_masked_linear.pt"))
+    h, w, mask, dy = masked_linear_golden_inputs()
+    assert torch.allclose(O.masked_linear_fwd(h, w, mask), gold["out"], rtol=1e-5, atol=1e-5)
+    gx, gw = O.masked_linear_bwd(dy, h, w, mask)
+    assert torch.allclose(gx, gold["dx"], rtol=1e-5, atol=1e-5) and torch.allclose(gw, gold["dw"], rtol=1e-5, atol=1e-5)
+    unmasked = ~mask[0]
+    assert not gold["dx"][unmasked].any()
+
+
 def _hf_qwen2_layer(cfg, w, i=0):
     from transformers import Qwen2Config
     from transformers.models.qwen2 import modeling_qwen2 as Q
