@@ -352,3 +352,44 @@ def load_megatron_masked_linear():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.LinearWithGradAccumulationAndAsyncCommunication
+
+
+def load_megatron_generation(cp_size: int, cp_rank: int, group=None):
+    """The reference's `long_vita_megatron/inference/text_generation/generation.py` (its inference-side
+    `get_batch_on_this_cp_rank` :517-539 and `sync_output` :542-566: all-gather of the ranks' zig-zag shards and
+    the un-permutation to global order), executed from /root/reference; `mpu` stand-ins report `cp_size`,
+    `cp_rank` and `group`.  Returns the module."""
+    import importlib.machinery
+
+    utils_mod, _ = load_megatron_training_utils(cp_size, cp_rank, 0)
+
+    def mk(name, **attrs):
+        m = sys.modules.get(name)
+        if m is None:
+            m = types.ModuleType(name)
+            m.__spec__ = importlib.machinery.ModuleSpec(name, loader=None)
+            m.__path__ = []
+            sys.modules[name] = m
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        return m
+
+    none = lambda *a, **k: None   # noqa: E731
+    mk("megatron.training", get_tokenizer=none)
+    mpu = sys.modules["megatron.core.mpu"]
+    mpu.get_context_parallel_group = lambda: group
+    mk("megatron.inference")
+    mk("megatron.inference.text_generation")
+    mk("megatron.inference.text_generation.communication", copy_from_last_to_first_pipeline_stage=none,
+       broadcast_from_last_pipeline_stage=none, broadcast_from_last_to_first_pipeline_stage=none)
+    mk("megatron.inference.text_generation.forward_step", ForwardStep=object)
+    mk("megatron.inference.text_generation.beam_utils", BeamHypotheses=object)
+    mk("megatron.inference.text_generation.generation", _build_attention_mask_and_position_ids=none)
+    for name in ("long_vita_megatron", "long_vita_megatron.training"):
+        mk(name)
+    sys.modules["long_vita_megatron.training.utils"] = utils_mod
+    path = os.path.join(REF_ROOT, "long_vita_megatron", "inference", "text_generation", "generation.py")
+    spec = importlib.util.spec_from_file_location("lv_ref_megatron_generation", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
