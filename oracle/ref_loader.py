@@ -393,3 +393,56 @@ def load_megatron_generation(cp_size: int, cp_rank: int, group=None):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_checkpoint_converter():
+    """`convert_checkpoint_from_megatron_to_transformers` and `safe_copy` of the reference's
+    tools/hf2mcore_long_vita.py (:120-124, :373-510).  The script is a concatenation of files whose mid-file
+    imports need a full Megatron install, so only these two function definitions are taken: their source text is
+    read from /root/reference at call time (never stored) and executed in a namespace that holds `torch`.
+    Returns the converter function."""
+    import ast
+
+    import torch
+
+    path = os.path.join(REF_ROOT, "tools", "hf2mcore_long_vita.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    wanted = {"safe_copy", "convert_checkpoint_from_megatron_to_transformers"}
+    lines = src.splitlines()
+    ns = {"torch": torch}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in wanted:
+            start = min([node.lineno] + [d.lineno for d in node.decorator_list]) - 1
+            code = "\n".join(lines[start : node.end_lineno])
+            exec(compile(code, f"{path}:{node.name}", "exec"), ns)     # noqa: S102 - the reference's own function
+    return ns["convert_checkpoint_from_megatron_to_transformers"]
+
+
+def module_tree_from_state_dict(sd):
+    """A torch.nn.Module tree whose attribute paths are the dotted keys of `sd` (numeric path components become
+    ModuleLists) - the shape of object the reference's converter walks (`mgmodel.decoder.layers[i]...`)."""
+    import torch
+
+    class Box(torch.nn.Module):
+        pass
+
+    root = Box()
+    for key, t in sd.items():
+        parts = key.split(".")
+        cur = root
+        for p in parts[:-1]:
+            if p not in cur._modules:
+                cur.add_module(p, Box())
+            cur = cur._modules[p]
+        cur.register_parameter(parts[-1], torch.nn.Parameter(t.clone(), requires_grad=False))
+
+    def listify(mod):
+        for name, child in list(mod._modules.items()):
+            listify(child)
+            names = list(child._modules)
+            if names and all(n.isdigit() for n in names) and not child._parameters:
+                mod._modules[name] = torch.nn.ModuleList([child._modules[str(i)] for i in range(len(names))])
+
+    listify(root)
+    return root

@@ -349,3 +349,33 @@ def test_masked_lm_head_forward_and_dgrad_equal_the_references_own_function():
     assert out.shape == gold["out"].shape and rel_fro(out, gold["out"]) < 8e-3      # bf16 inputs vs the fp32 fixture
     assert dx.shape == gold["dx"].shape and rel_fro(dx, gold["dx"]) < 8e-3
     assert torch.equal(dx[:, 0].float().abs().sum(-1) == 0, gold["dx"][:, 0].abs().sum(-1) == 0)   # same zero rows
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference"), reason="/root/reference not mounted (GPU box)")
+def test_checkpoint_layout_is_the_inverse_of_the_references_own_converter():
+    """Live: the reference's `convert_checkpoint_from_megatron_to_transformers` (tools/hf2mcore_long_vita.py:373-510,
+    executed from /root/reference) walks a Megatron-shaped module tree built from `checkpoint.hf_to_mcore(hf)` and
+    fills the reference's own HF model; that model's state dict must be `hf` again, bit for bit - so our mcore names
+    and row orders are exactly the ones the reference's converter reads.  (The converter hard-codes the ViT
+    geometry 1024 / 16 heads, so the vision tower has the real width here.)"""
+    import types
+    from dataclasses import replace
+
+    from oracle import ref_loader
+
+    base = LongVITAConfig.tiny(layers=2, vit_layers=1)
+    cfg = replace(base, visual=replace(base.visual, hidden_size=1024, num_attention_heads=16, intermediate_size=64))
+    hf = synthetic_state_dict(cfg, seed=404, dtype=torch.float32, perturb=True)
+    mg = ref_loader.module_tree_from_state_dict(ck.hf_to_mcore(hf, cfg))
+    hfmodel = ref_loader.build_reference_long_vita(cfg, {k: torch.zeros_like(v) for k, v in hf.items()})
+    args = types.SimpleNamespace(
+        fp16=False, bf16=False, num_query_groups=cfg.num_key_value_heads, hidden_size=cfg.hidden_size,
+        num_attention_heads=cfg.num_attention_heads, transformer_impl="transformer_engine", ffn_hidden_size=cfg.intermediate_size,
+        untie_embeddings_and_output_weights=True,
+        vit_args=types.SimpleNamespace(hidden_size=1024, num_query_groups=16, num_attention_heads=16))
+    convert = ref_loader.load_checkpoint_converter()
+    convert(mg, hfmodel, args)                     # asserts internally that every parameter was copied exactly once
+    got = hfmodel.state_dict()
+    assert set(got) == set(hf)
+    for k in hf:
+        assert torch.equal(got[k], hf[k]), k
