@@ -446,3 +446,29 @@ def module_tree_from_state_dict(sd):
 
     listify(root)
     return root
+
+
+def load_class_methods(rel_path: str, class_name: str, method_names, namespace=None):
+    """Methods of a class of the reference, taken by name from the file's syntax tree (source text read from
+    /root/reference at call time, never stored) and executed as plain functions in a namespace holding `torch` -
+    for files whose module-level imports need a full Megatron install.  Returns {name: function(self, ...)}."""
+    import ast
+
+    import torch
+
+    path = os.path.join(REF_ROOT, rel_path)
+    src = open(path).read()
+    lines = src.splitlines()
+    ns = {"torch": torch}
+    ns.update(namespace or {})          # names the methods' annotations / bodies expect at module level
+    out = {}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name == class_name:
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name in method_names:
+                    body = "\n".join(lines[item.lineno - 1 : item.end_lineno])
+                    import textwrap
+
+                    exec(compile(textwrap.dedent(body), f"{path}:{class_name}.{item.name}", "exec"), ns)   # noqa: S102
+                    out[item.name] = ns[item.name]
+    return out

@@ -379,3 +379,89 @@ def test_checkpoint_layout_is_the_inverse_of_the_references_own_converter():
     assert set(got) == set(hf)
     for k in hf:
         assert torch.equal(got[k], hf[k]), k
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference"), reason="/root/reference not mounted (GPU box)")
+def test_forward_glue_equals_the_references_own_gptvl_forward(tiny, model):
+    """Live: the reference's `GPTVLModel.forward` (gpt_vl_model.py:233-416) is executed from /root/reference on a
+    stand-in `self` whose sub-modules are the reference's OWN LanguageModelEmbedding and RotaryEmbedding, plus this
+    build's vision tower / decoder layers / output GEMM for the arithmetic in between.  Everything the
+    two forwards do around those calls - external_inputs routing, the embedding merge, rotary table, logit_mask,
+    labels masked_select, [s b h] -> [b s h] - must then agree bit for bit with B200GPTVLModel.forward."""
+    import os
+    import types
+
+    from oracle import ref_loader
+
+    cfg, hf, mc = tiny
+    ids, images, idx = _inputs(cfg)
+    s = ids.shape[1]
+    args = types.SimpleNamespace(output_multiplier_scale=None, output_logit_softcapping=None, is_instruction_dataset=False)
+    ref_forward = ref_loader.load_class_methods(
+        "long_vita_megatron/core/models/multimodal/gpt_vl_model.py", "GPTVLModel", {"forward"},
+        namespace={"Tensor": torch.Tensor, "InferenceParams": object, "PackedSeqParams": object, "get_args": lambda: args,
+                   "os": os})["forward"]
+    emb_cls = ref_loader.load_megatron_embedding()
+    ecfg = types.SimpleNamespace(hidden_size=cfg.hidden_size, hidden_dropout=0.0, fp32_residual_connection=False,
+                                 sequence_parallel=False, init_method=lambda w: None, perform_initialization=False,
+                                 clone_scatter_output_in_embedding=False)
+    embedding = emb_cls(ecfg, vocab_size=cfg.vocab_size, max_sequence_length=4096, position_embedding_type="rope",
+                        parallel_word_embedding=False).eval()
+    embedding.word_embeddings.weight.data = model.word_embeddings.clone()
+    rope_mod, cpu_placement = ref_loader.load_megatron_rope(1, 0)
+    with cpu_placement():
+        rotary = rope_mod.RotaryEmbedding(kv_channels=cfg.head_dim, rotary_percent=1.0, rotary_base=int(cfg.rope_theta))
+    rotary.get_rotary_seq_len = lambda inference_params, decoder, decoder_input, config: decoder_input.shape[0]
+
+    def decoder(hidden_states, attention_mask, inference_params, rotary_pos_emb, packed_seq_params):
+        from long_vita_b200 import ops
+
+        f = rotary_pos_emb.reshape(rotary_pos_emb.shape[0], -1)
+        cos, sin = torch.cos(f).to(torch.bfloat16), torch.sin(f).to(torch.bfloat16)
+        x, delta = hidden_states[:, 0], None
+        for layer in model.layers:
+            x, delta = layer.forward(x, delta, cos, sin, {})
+        h, _ = ops.rmsnorm(delta, model.final_layernorm, cfg.rms_norm_eps, residual=x)
+        return h.unsqueeze(1)
+
+    def output_layer(hidden_states, weight=None, logit_mask=None):
+        from long_vita_b200 import ops
+
+        if logit_mask is None:
+            return ops.linear(hidden_states, model.output_weight), None
+        sel = torch.masked_select(hidden_states, logit_mask.transpose(0, 1).unsqueeze(2)).reshape(-1, 1, hidden_states.shape[2])
+        return ops.linear(sel, model.output_weight), None        # same rows the reference's masked linear selects
+
+    def loss_fn(labels, logits):
+        lg = logits.float().transpose(0, 1)
+        return torch.nn.functional.cross_entropy(lg.reshape(-1, lg.shape[-1]), labels.reshape(-1), reduction="none").view(labels.shape)
+
+    me = types.SimpleNamespace(
+        pre_process=True, post_process=True, external_feature_model=lambda **kw: model.external_feature_model(**kw),
+        embedding=embedding, position_embedding_type="rope", rotary_pos_emb=rotary, decoder=decoder, config=None,
+        unused=torch.zeros(cfg.hidden_size, dtype=torch.bfloat16), share_embeddings_and_output_weights=False,
+        output_layer=output_layer, compute_language_model_loss=loss_fn)
+    mask = torch.zeros(1, s, dtype=torch.bool)
+    mask[0, 270:] = True
+    labels = torch.randint(0, cfg.vocab_size, (1, s), generator=torch.Generator().manual_seed(1))
+    pos = torch.arange(s).unsqueeze(0)
+    ext = {"images": images, "indices": idx}
+    ip = types.SimpleNamespace(external_inputs=ext, key_value_memory_dict={}, logit_mask=mask, use_kv_cache=False)
+    import socket
+
+    import torch.distributed as dist
+
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    dist.init_process_group("gloo", rank=0, world_size=1, init_method=f"tcp://127.0.0.1:{port}")   # forward asks get_rank()
+    try:
+        with oracle_ops(), cpu_placement():
+            cases = [dict(external_inputs=ext), dict(external_inputs=ext, logit_mask=mask), dict(inference_params=ip),
+                     dict(external_inputs=ext, logit_mask=mask, labels=labels), dict()]
+            for kw in cases:
+                want = ref_forward(me, ids, pos, None, **kw)
+                got = model(ids, pos, None, **kw)
+                assert got.shape == want.shape and torch.equal(got, want), sorted(kw)
+    finally:
+        dist.destroy_process_group()

@@ -277,3 +277,20 @@ def test_whole_model_oracle_runs_and_uses_image_features():
     c = OM.long_vita_forward(cfg, w, ids, None, None, num_logits_to_keep=1)
     assert a.shape == (1, 1, cfg.vocab_size)
     assert not torch.allclose(a, b) and not torch.allclose(a, c)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted (GPU box)")
+def test_live_megatron_vision_downsample_matches_oracle_bit_exact():
+    """The Megatron twin of the projector's front end - MegatronVisionModel.forward_downsample / pixel_shuffle
+    (long_vita_megatron/pretrain_long_vita.py:467-483, 572-582), executed from /root/reference: drop the class
+    token, view as [n, 32, 32, C], pixel-shuffle x0.5."""
+    import types
+
+    m = ref_loader.load_class_methods("long_vita_megatron/pretrain_long_vita.py", "MegatronVisionModel",
+                                      {"forward_downsample", "pixel_shuffle"})
+    me = types.SimpleNamespace(add_class_token=True, vision_downsample_ratio=0.5, vision_downsample_stride=1)
+    me.pixel_shuffle = lambda x, scale_factor=0.5: m["pixel_shuffle"](me, x, scale_factor)
+    x = torch.arange(2 * 17 * 6, dtype=torch.int32).reshape(2, 17, 6)               # 1 class token + 4 x 4 patches
+    want = m["forward_downsample"](me, x)
+    got = O.pixel_shuffle_half(x[:, 1:].reshape(2, 4, 4, 6)).reshape(2, 4, 24)
+    assert torch.equal(got, want)
