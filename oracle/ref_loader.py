@@ -98,7 +98,8 @@ def load_long_vita():
       2. `Qwen2Model._update_causal_mask` (called at :162) was removed -> replaced by the explicit
          additive causal mask [1, 1, s, s] it used to return for eager / sdpa attention;
       3. `Qwen2DecoderLayer.forward` now returns a tensor, the reference indexes `layer_outputs[0]`
-         (:204) as under 4.48 -> each layer's forward is wrapped to return a 1-tuple
+         (:204) as under 4.48, and the cache keyword was renamed `past_key_value` -> `past_key_values`
+         (:196) -> each layer's forward is wrapped to return a 1-tuple and to accept the old keyword
          (`wrap_decoder_layers(model)`, call it after constructing the model).
     With these the unmodified reference forward runs on CPU (`attn_implementation="eager"`,
     `use_flash_attn=False` in the visual config)."""
@@ -114,8 +115,9 @@ def load_long_vita():
 
     def _update_causal_mask(self, attention_mask, input_tensor, cache_position, past_key_values, output_attentions=False):
         s = input_tensor.shape[1]
-        m = torch.full((s, s), torch.finfo(input_tensor.dtype).min, dtype=input_tensor.dtype, device=input_tensor.device)
-        return torch.triu(m, diagonal=1)[None, None]
+        past = past_key_values.get_seq_length() if past_key_values is not None else 0
+        m = torch.full((s, past + s), torch.finfo(input_tensor.dtype).min, dtype=input_tensor.dtype, device=input_tensor.device)
+        return torch.triu(m, diagonal=past + 1)[None, None]          # key j hidden from new row i iff j > past + i
 
     if not hasattr(mod.LongVITAModel, "_update_causal_mask"):
         mod.LongVITAModel._update_causal_mask = _update_causal_mask
@@ -125,6 +127,8 @@ def load_long_vita():
             orig = layer.forward
 
             def fwd(*a, _orig=orig, **k):
+                if "past_key_value" in k:                 # 4.48 keyword; 5.x renamed it (and would swallow the old one)
+                    k["past_key_values"] = k.pop("past_key_value")
                 out = _orig(*a, **k)
                 return out if isinstance(out, tuple) else (out,)
 

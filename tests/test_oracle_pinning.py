@@ -118,6 +118,23 @@ def test_live_reference_cp_function_reproduces_the_shard_golden():
     assert torch.arange(3, device="cpu").device.type == "cpu" and torch.tensor([1]).sum() == 1   # patches were undone
 
 
+def test_oracle_full_forward_equals_the_references_incremental_decoding():
+    """The reference's own KV-cache decoding (three single-token steps after a use_cache prefill,
+    tests/golden/ref_long_vita_decode.pt) gives the logits of a full forward over the extended sequence - which is
+    what the oracle computes.  This is the fixture the decode path of the build is checked against."""
+    from make_golden import decode_new_tokens
+
+    gold, cfg, w, ids, images, idx = _long_vita_golden()
+    dec = torch.load(os.path.join(GOLD, "ref_long_vita_decode.pt"))
+    new = decode_new_tokens(cfg)
+    s = ids.shape[1]
+    assert dec["cache_len"] == s + new.shape[1]
+    logits = OM.long_vita_forward(cfg, w, torch.cat([ids, new], dim=1), images, idx)[0]
+    assert torch.allclose(logits[s - 1], dec["prefill_last"], rtol=2e-4, atol=2e-4)
+    for i in range(new.shape[1]):
+        assert torch.allclose(logits[s + i], dec["steps"][i], rtol=2e-4, atol=2e-4), i
+
+
 def test_rope_matches_the_references_own_megatron_rope():
     """oracle rope tables / apply against the reference's Megatron RotaryEmbedding.forward and
     apply_rotary_pos_emb_bshd (rotary_pos_embedding.py:84-122, 181-204) - bit-exact - and the zig-zag slice of the
