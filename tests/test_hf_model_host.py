@@ -103,3 +103,9 @@ def test_product_composition_against_the_references_own_forward():
     rows = gold["rows"]
     for li in range(cfg.num_hidden_layers + 1):
         assert rel_fro(out.hidden_states[li][0][rows], gold["hidden_rows"][li]) < 1.5e-2, li
+    # labels -> loss: the reference's ForCausalLMLoss (shift by one, mean over the labels that are not -100)
+    from make_golden import golden_labels
+
+    with oracle_ops():
+        loss = model(input_ids=ids, images=images.to(torch.bfloat16), image_indices=idx, labels=golden_labels(ids)).loss
+    assert abs(float(loss) - float(gold["loss"])) < 2e-2 * float(gold["loss"]), (float(loss), float(gold["loss"]))

@@ -87,6 +87,13 @@ def test_whole_model_oracle_matches_the_references_own_forward():
     assert torch.allclose(h_final[rows], ref_h[-1], rtol=2e-4, atol=2e-4)
     assert torch.allclose(logits[0], gold["logits_last8"], rtol=2e-4, atol=2e-4), float((logits[0] - gold["logits_last8"]).abs().max())
     assert float((logits[0] - gold["logits_last8"]).norm() / gold["logits_last8"].norm()) < 1e-5
+    # the loss the reference returns for `labels` (shifted, -100 ignored) from the oracle's full logits
+    from make_golden import golden_labels
+
+    full = OM.long_vita_forward(cfg, w, ids, images, idx)[0]
+    labels = golden_labels(ids)[0]
+    want = torch.nn.functional.cross_entropy(full[:-1].float(), labels[1:], ignore_index=-100)
+    assert abs(float(want) - float(gold["loss"])) < 1e-4
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted (GPU box)")
