@@ -318,3 +318,27 @@ def test_live_megatron_vision_downsample_matches_oracle_bit_exact():
     want = m["forward_downsample"](me, x)
     got = O.pixel_shuffle_half(x[:, 1:].reshape(2, 4, 4, 6)).reshape(2, 4, 24)
     assert torch.equal(got, want)
+
+
+def test_attention_forward_and_grads_match_transformers_eager_attention():
+    """The attention the reference's HF path delegates to when flash-attn is absent - transformers'
+    `eager_attention_forward` (repeat_kv + softmax(QK^T * scaling + causal mask) V) - and its autograd, against
+    oracle.ops.attention / attention_grads (causal GQA 5:1)."""
+    import types
+
+    from transformers.models.qwen2.modeling_qwen2 import eager_attention_forward
+
+    g = torch.Generator().manual_seed(17)
+    b, s, hq, hkv, d = 1, 96, 10, 2, 32
+    q, k, v = (torch.randn(b, s, h, d, generator=g) for h in (hq, hkv, hkv))
+    do = torch.randn(b, s, hq, d, generator=g)
+    qq, kk, vv = (t.clone().transpose(1, 2).requires_grad_(True) for t in (q, k, v))          # [b, h, s, d]
+    mask = torch.triu(torch.full((s, s), torch.finfo(torch.float32).min), diagonal=1)[None, None]
+    mod = types.SimpleNamespace(num_key_value_groups=hq // hkv, training=False)
+    out, _ = eager_attention_forward(mod, qq, kk, vv, mask, scaling=d ** -0.5, dropout=0.0)   # [b, s, h, d]
+    out.backward(do)
+    ref, _ = O.attention(q, k, v, causal=True)
+    assert torch.allclose(ref, out.detach(), rtol=1e-5, atol=1e-5)
+    dq, dk, dv = O.attention_grads(q, k, v, do, causal=True)
+    for a, r in ((dq, qq.grad), (dk, kk.grad), (dv, vv.grad)):
+        assert torch.allclose(a, r.transpose(1, 2), rtol=1e-4, atol=1e-5)
