@@ -26,7 +26,6 @@ sequence the reference would execute on CPU).
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, Optional
 
 import torch

@@ -11,7 +11,6 @@ Outside this context manager the product path is untouched and still fails loudl
 from __future__ import annotations
 
 import contextlib
-import math
 
 import torch
 import torch.nn.functional as F

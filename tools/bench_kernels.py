@@ -6,7 +6,6 @@ build, cuDNN SDPA, cuBLAS via torch.matmul).  Writes gpurun_out/kernels.json.
 """
 import argparse
 import json
-import math
 import os
 import sys
 
