@@ -62,3 +62,49 @@ def test_ops_refuse_cpu_tensors(lib_built):
     x = torch.zeros(4, 16, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.swiglu(x)
+
+
+def _attn_params(**kw):
+    from long_vita_b200._lib import AttnParams
+
+    p = AttnParams()
+    p.q = p.k = p.v = p.out = 0x1000                    # never dereferenced: every case below fails validation first
+    p.lse = None
+    p.batch, p.sq, p.sk, p.hq, p.hkv, p.d = 1, 256, 256, 8, 2, 128
+    for arr, row in ((p.q_strides, 8 * 128), (p.k_strides, 2 * 128), (p.v_strides, 2 * 128), (p.o_strides, 8 * 128)):
+        arr[0], arr[1], arr[2] = 256 * row, row, 128
+    p.scale, p.causal, p.q_seg_len, p.kv_pos0 = 0.088, 1, 256, 0
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+@pytest.mark.parametrize("kw,msg", [
+    (dict(d=96), b"head_dim 96 not supported"),
+    (dict(hq=7), b"not a multiple of hkv"),
+    (dict(sq=0), b"empty shape"),
+    (dict(q=None), b"null tensor pointer"),
+    (dict(q_seg_len=300), b"out of range"),
+    (dict(q_seg_len=100), b"q_seg_len % 128 == 0"),
+])
+def test_attention_argument_errors_have_the_documented_code_and_text(lib_built, kw, msg):
+    """every entry point returns a negative LV_E* code and sets lv_last_error()."""
+    from long_vita_b200 import _lib
+
+    h = _lib.lib()
+    p = _attn_params(**kw)
+    rc = h.lv_attn_fwd(ctypes.byref(p), None)
+    assert rc == -1 and msg in h.lv_last_error(), h.lv_last_error()
+    with pytest.raises(RuntimeError, match="lv_attn_fwd failed"):
+        _lib.check(rc, "lv_attn_fwd")
+
+
+def test_backward_and_gemm_argument_errors(lib_built):
+    from long_vita_b200 import _lib
+    from long_vita_b200._lib import AttnBwdParams
+
+    h = _lib.lib()
+    b = AttnBwdParams()
+    assert h.lv_attn_bwd(ctypes.byref(b), None) == -1 and b"required" in h.lv_last_error()
+    assert h.lv_gemm_bias_act(1, 1, None, 1, 4, 24, 8, 8, 8, 24, 3, None) == -1 and b"SwiGLU" in h.lv_last_error()
+    assert h.lv_gemm_bias_act(1, 1, None, 1, 4, 16, 8, 8, 8, 16, 7, None) == -1 and b"unknown activation" in h.lv_last_error()
