@@ -137,7 +137,9 @@ def cast_weights(w: Dict[str, torch.Tensor], dtype) -> Dict[str, torch.Tensor]:
 
 def siglip_forward(cfg, w: Dict[str, torch.Tensor], images: torch.Tensor, prefix: str = ""):
     """SigLIPViTModel.forward (long_vita_megatron/core/models/vision/siglip_vit_model.py:165-228) with the
-    block of :29-86 and the geometry of pretrain_long_vita.py:268-307.  `cfg` has hidden_size,
+    block of :29-86 and the geometry of pretrain_long_vita.py:268-307.  Pinned (tests/test_oracle_pinning.py) against
+    the HF SigLIP vision encoder the Megatron weights are converted from (transformers SiglipVisionModel, last hidden
+    state before post_layernorm - the Megatron model omits that norm, siglip_vit_model.py:141-142).  `cfg` has hidden_size,
     num_attention_heads, kv_channels, num_layers, patch_dim, layernorm_epsilon.  linear_qkv rows are
     Megatron's per-head interleave [head, (q, k, v), hn]."""
     H, hn, C = cfg.num_attention_heads, cfg.kv_channels, cfg.hidden_size

@@ -342,3 +342,42 @@ def test_attention_forward_and_grads_match_transformers_eager_attention():
     dq, dk, dv = O.attention_grads(q, k, v, do, causal=True)
     for a, r in ((dq, qq.grad), (dk, kk.grad), (dv, vv.grad)):
         assert torch.allclose(a, r.transpose(1, 2), rtol=1e-4, atol=1e-5)
+
+
+def test_siglip_tower_matches_transformers_siglip_encoder():
+    """a9: oracle.model.siglip_forward (the Megatron SigLIPViTModel of siglip_vit_model.py:165-228: conv patch embed +
+    learned positions, pre-LN blocks with tanh-GELU, no class token, NO final layer norm) against the HF SigLIP vision
+    encoder the Megatron weights are converted from - its last hidden state before `post_layernorm`.  The q/k/v
+    projections are re-laid into Megatron's per-head interleave [head, (q, k, v), hn]."""
+    from types import SimpleNamespace
+
+    from transformers import SiglipVisionConfig, SiglipVisionModel
+
+    torch.manual_seed(3)
+    C, I, H, L = 144, 304, 2, 2                       # head_dim 72, as the real SigLIP-so400m
+    hf = SiglipVisionModel(SiglipVisionConfig(hidden_size=C, intermediate_size=I, num_hidden_layers=L, num_attention_heads=H,
+                                              image_size=448, patch_size=14, hidden_act="gelu_pytorch_tanh",
+                                              layer_norm_eps=1e-6, attn_implementation="eager")).eval()
+    sd = hf.state_dict()
+    e = "vision_model."
+    hn = C // H
+    w = {"conv1.weight": sd[e + "embeddings.patch_embedding.weight"], "conv1.bias": sd[e + "embeddings.patch_embedding.bias"],
+         "position_embeddings.weight": sd[e + "embeddings.position_embedding.weight"]}
+    for i in range(L):
+        h, m = f"{e}encoder.layers.{i}.", f"decoder.layers.{i}."
+        qkv_w = torch.stack([sd[h + f"self_attn.{n}_proj.weight"].view(H, hn, C) for n in "qkv"], dim=1).reshape(3 * C, C)
+        qkv_b = torch.stack([sd[h + f"self_attn.{n}_proj.bias"].view(H, hn) for n in "qkv"], dim=1).reshape(3 * C)
+        w.update({m + "input_layernorm.weight": sd[h + "layer_norm1.weight"], m + "input_layernorm.bias": sd[h + "layer_norm1.bias"],
+                  m + "self_attention.linear_qkv.weight": qkv_w, m + "self_attention.linear_qkv.bias": qkv_b,
+                  m + "self_attention.linear_proj.weight": sd[h + "self_attn.out_proj.weight"],
+                  m + "self_attention.linear_proj.bias": sd[h + "self_attn.out_proj.bias"],
+                  m + "pre_mlp_layernorm.weight": sd[h + "layer_norm2.weight"], m + "pre_mlp_layernorm.bias": sd[h + "layer_norm2.bias"],
+                  m + "mlp.linear_fc1.weight": sd[h + "mlp.fc1.weight"], m + "mlp.linear_fc1.bias": sd[h + "mlp.fc1.bias"],
+                  m + "mlp.linear_fc2.weight": sd[h + "mlp.fc2.weight"], m + "mlp.linear_fc2.bias": sd[h + "mlp.fc2.bias"]})
+    images = torch.randn(2, 3, 448, 448, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        ref = hf(pixel_values=images, output_hidden_states=True).hidden_states[-1]
+    cfg = SimpleNamespace(hidden_size=C, num_attention_heads=H, kv_channels=hn, num_layers=L, patch_dim=14, layernorm_epsilon=1e-6)
+    out = OM.siglip_forward(cfg, w, images)
+    assert out.shape == ref.shape == (2, 1024, C)
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-4), float((out - ref).abs().max())
