@@ -381,3 +381,19 @@ def test_siglip_tower_matches_transformers_siglip_encoder():
     out = OM.siglip_forward(cfg, w, images)
     assert out.shape == ref.shape == (2, 1024, C)
     assert torch.allclose(out, ref, rtol=1e-4, atol=1e-4), float((out - ref).abs().max())
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted (GPU box)")
+def test_live_megatron_local_rmsnorm_matches_oracle_bit_exact():
+    """a5: the reference's Megatron-local RMSNorm (core/transformer/custom_layers/transformer_engine.py:54-79:
+    `_norm(x.float()).type_as(x) * weight`), executed from /root/reference, against oracle.ops.rmsnorm in bf16."""
+    import types
+
+    m = ref_loader.load_class_methods("long_vita_megatron/core/transformer/custom_layers/transformer_engine.py", "RMSNorm",
+                                      {"_norm", "forward"})
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn(37, 640, generator=g) * 3).to(torch.bfloat16)
+    w = (1 + 0.1 * torch.randn(640, generator=g)).to(torch.bfloat16)
+    me = types.SimpleNamespace(eps=1e-6, weight=w)
+    me._norm = lambda t: m["_norm"](me, t)
+    assert torch.equal(m["forward"](me, x), O.rmsnorm(x, w, 1e-6))
