@@ -108,3 +108,19 @@ def test_backward_and_gemm_argument_errors(lib_built):
     assert h.lv_attn_bwd(ctypes.byref(b), None) == -1 and b"required" in h.lv_last_error()
     assert h.lv_gemm_bias_act(1, 1, None, 1, 4, 24, 8, 8, 8, 24, 3, None) == -1 and b"SwiGLU" in h.lv_last_error()
     assert h.lv_gemm_bias_act(1, 1, None, 1, 4, 16, 8, 8, 8, 16, 7, None) == -1 and b"unknown activation" in h.lv_last_error()
+
+
+def test_missing_extension_fails_loudly(monkeypatch):
+    """No CPU / PyTorch fallback: without liblvb200.so every operator raises, naming the build command."""
+    from long_vita_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/liblvb200.so")
+    with pytest.raises(RuntimeError, match="is missing"):
+        _lib.lib()
+    from long_vita_b200 import ops
+
+    with pytest.raises(RuntimeError):
+        ops.launch_count()
+    monkeypatch.undo()
+    assert _lib.lib().lv_version() >= 1000
