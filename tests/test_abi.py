@@ -124,3 +124,25 @@ def test_missing_extension_fails_loudly(monkeypatch):
         ops.launch_count()
     monkeypatch.undo()
     assert _lib.lib().lv_version() >= 1000
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use it."""
+    import ast
+
+    pkg = os.path.join(ROOT, "long-vita_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            tree = ast.parse(open(os.path.join(dirpath, f)).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom) and node.level == 0:
+                    names = [node.module or ""]
+                if any(n == "oracle" or n.startswith("oracle.") or n == "tests" or n.startswith("tests.") for n in names):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
