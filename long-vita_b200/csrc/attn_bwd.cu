@@ -235,22 +235,26 @@ __global__ void __launch_bounds__(128, 1)
       mbar_wait(&str_full[stage], n_str[stage] & 1);
       ++n_str[stage];
       __syncthreads();   // column statistics of this stage are visible to every thread
-      // ---- MMA phase 1: the two SS GEMMs ----
-      if (tid == 0) {
+      // ---- MMA phase 1: the two SS GEMMs (warp 0, warp-uniform; one elected lane issues) ----
+      if (warp == 0) {
         tc_fence_after();
-        const uint32_t r0 = smem_u32(sR0), r1 = smem_u32(sR1);
-        const uint32_t s0 = smem_u32(sS0 + stage * TILE), s1 = smem_u32(sS1 + stage * TILE);
+        const uint64_t r0 = make_smem_desc(smem_u32(sR0), 16, 1024), r1 = make_smem_desc(smem_u32(sR1), 16, 1024);
+        const uint64_t s0 = make_smem_desc(smem_u32(sS0 + stage * TILE), 16, 1024);
+        const uint64_t s1 = make_smem_desc(smem_u32(sS1 + stage * TILE), 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
-          umma_ss(tA, make_smem_desc(r0 + off, 16, 1024), make_smem_desc(s0 + off, 16, 1024), idesc_ss, kk != 0);
-        }
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = ((kk / 4) * 16384 + (kk % 4) * 32) >> 4;
+            umma_ss(tA, r0 + off, s0 + off, idesc_ss, kk != 0);
+          }
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
-          umma_ss(tB, make_smem_desc(r1 + off, 16, 1024), make_smem_desc(s1 + off, 16, 1024), idesc_ss, kk != 0);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = ((kk / 4) * 16384 + (kk % 4) * 32) >> 4;
+            umma_ss(tB, r1 + off, s1 + off, idesc_ss, kk != 0);
+          }
+          umma_commit(mma1);
         }
-        umma_commit(mma1);
+        __syncwarp();
       }
       mbar_wait(mma1, n_mma1 & 1);
       ++n_mma1;
@@ -300,24 +304,28 @@ __global__ void __launch_bounds__(128, 1)
       tc_fence_before();
       __syncthreads();
 
-      // ---- MMA phase 2: TS GEMMs into the accumulators ----
-      if (tid == 0) {
+      // ---- MMA phase 2: TS GEMMs into the accumulators (warp 0, one elected lane issues) ----
+      if (warp == 0) {
         tc_fence_after();
-        const uint32_t s0 = smem_u32(sS0 + stage * TILE), s1 = smem_u32(sS1 + stage * TILE);
+        const uint64_t s0 = make_smem_desc(smem_u32(sS0 + stage * TILE), 16384, 1024);
+        const uint64_t s1 = make_smem_desc(smem_u32(sS1 + stage * TILE), 16384, 1024);
         const uint32_t acc = first ? 0u : 1u;
-        if (MODE == 0) {
+        if (elect_one()) {
+          if (MODE == 0) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dV += P^T dO
-            umma_ts(tAcc0, tA + kk * 8, make_smem_desc(s1 + kk * 2048, 16384, 1024), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
+            for (int kk = 0; kk < 8; ++kk)   // dV += P^T dO
+              umma_ts(tAcc0, tA + kk * 8, s1 + (uint64_t)(kk * 128), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dK += dS^T Q
-            umma_ts(tAcc1, tB + kk * 8, make_smem_desc(s0 + kk * 2048, 16384, 1024), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
-        } else {
+            for (int kk = 0; kk < 8; ++kk)   // dK += dS^T Q
+              umma_ts(tAcc1, tB + kk * 8, s0 + (uint64_t)(kk * 128), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
+          } else {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dQ += dS K
-            umma_ts(tAcc0, tB + kk * 8, make_smem_desc(s0 + kk * 2048, 16384, 1024), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
+            for (int kk = 0; kk < 8; ++kk)   // dQ += dS K
+              umma_ts(tAcc0, tB + kk * 8, s0 + (uint64_t)(kk * 128), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
+          }
+          umma_commit(mma2);
         }
-        umma_commit(mma2);
+        __syncwarp();
         // the streamed stage (and, for the next item, the resident tiles) may be overwritten only
         // after these MMAs have read them
         mbar_wait(mma2, n_mma2 & 1);

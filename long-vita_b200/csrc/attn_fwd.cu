@@ -339,7 +339,12 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-    if (lane == 0) {
+    {
+      // The whole warp executes this warp-uniform control flow and ONE elected lane issues the
+      // tcgen05 instructions: descriptor arithmetic then lives in uniform registers.  (With the issue
+      // loop under `if (lane == 0)` the compiler wrapped every MMA in an ELECT / R2UR.BROADCAST /
+      // BRA.U.ANY sequence: ~73 issue cycles per 64-cycle MMA - the issuer was 64 % busy and bounded the
+      // kernel, profiles/README.md.)
       constexpr uint32_t idesc_qk = make_idesc_bf16(A_BM, A_BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(A_BM, D, 0, 1);
       const uint32_t tS[2] = {tmem_base + Cfg::TM_S0, tmem_base + Cfg::TM_S1};
@@ -347,18 +352,25 @@ __global__ void __launch_bounds__(A_THREADS, 1)
       uint32_t item_cnt = 0, kcnt = 0, vcnt_wait = 0, vcnt_rel = 0;
       uint32_t pcnt[2] = {0, 0};
 
+      // tiles are 1024-byte aligned, so stepping a descriptor is a plain add on its 14-bit address field
+      const uint64_t qdesc[2] = {make_smem_desc(smem_u32(sQ), 16, 1024), make_smem_desc(smem_u32(sQ + Cfg::TILE_BYTES), 16, 1024)};
+      const uint64_t kdesc0 = make_smem_desc(smem_u32(sK), 16, 1024);
+      const uint64_t vdesc0 = make_smem_desc(smem_u32(sV), 16384, 1024);
       auto issue_qk = [&](int t, int kst) {
-        const uint32_t qa = smem_u32(sQ + t * Cfg::TILE_BYTES);
-        const uint32_t ka = smem_u32(sK + kst * Cfg::TILE_BYTES);
+        const uint64_t qd = qdesc[t];
+        const uint64_t kd = kdesc0 + (uint64_t)((kst * Cfg::TILE_BYTES) >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
-          umma_ss(tS[t], make_smem_desc(qa + off, 16, 1024), make_smem_desc(ka + off, 16, 1024), idesc_qk,
-                  kk != 0 ? 1u : 0u);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = ((kk / 4) * 16384 + (kk % 4) * 32) >> 4;
+            umma_ss(tS[t], qd + off, kd + off, idesc_qk, kk != 0 ? 1u : 0u);
+          }
         }
+        __syncwarp();
       };
       auto issue_pv = [&](int t, int vst, bool accumulate) {
-        const uint32_t va = smem_u32(sV + vst * Cfg::TILE_BYTES);
+        const uint64_t vd = vdesc0 + (uint64_t)((vst * Cfg::TILE_BYTES) >> 4);
+        const bool leader = elect_one();
 #pragma unroll
         for (int kk = 0; kk < A_BN / 16; ++kk) {
           if (QH && (kk & 1) == 0) {
@@ -367,9 +379,13 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           }
           // A: P_t rows in TMEM, 16 bf16 (= 8 columns) per k-step.  B: V tile, MN-major: 16 key rows
           // (2 KB) per k-step, the second 64 head-dim columns live one 16 KB box further.
-          umma_ts(tO[t], tS[t] + kk * 8, make_smem_desc(va + kk * 2048, 16384, 1024), idesc_pv,
-                  (accumulate || kk != 0) ? 1u : 0u);
+          if (leader) umma_ts(tO[t], tS[t] + kk * 8, vd + (uint64_t)(kk * 128), idesc_pv, (accumulate || kk != 0) ? 1u : 0u);
         }
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
       };
 
       for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
@@ -389,7 +405,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           }
           if (j < n0) {
             issue_qk(0, kst);
-            umma_commit(&s_full[0]);
+            commit(&s_full[0]);
           }
           if (j >= 1) {
             if (j - 1 < n1) {
@@ -402,18 +418,18 @@ __global__ void __launch_bounds__(A_THREADS, 1)
               ++pcnt[1];
               tc_fence_after();
               issue_pv(1, vc % NS, j - 1 > 0);
-              if (j - 1 == n1 - 1) umma_commit(&o_full[1]);
+              if (j - 1 == n1 - 1) commit(&o_full[1]);
             }
             // V(j-1) has now been consumed by every PV that needs it
-            umma_commit(&v_empty[vcnt_rel % NS]);
+            commit(&v_empty[vcnt_rel % NS]);
             ++vcnt_rel;
           }
           if (j < n1) {
             issue_qk(1, kst);
-            umma_commit(&s_full[1]);
+            commit(&s_full[1]);
           }
           if (j < nmax) {
-            umma_commit(&k_empty[kst]);
+            commit(&k_empty[kst]);
             ++kcnt;
           }
           if (j < n0) {
@@ -426,7 +442,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
             ++pcnt[0];
             tc_fence_after();
             issue_pv(0, vc % NS, j > 0);
-            if (j == n0 - 1) umma_commit(&o_full[0]);
+            if (j == n0 - 1) commit(&o_full[0]);
           }
         }
       }
@@ -761,7 +777,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    {   // warp-uniform control flow; one elected lane issues (see the v1 kernel)
       constexpr uint32_t idesc_qk = make_idesc_bf16(A_BM, A_BH, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(A_BM, D, 0, 1);
       uint32_t item_cnt = 0;
@@ -785,16 +801,18 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           }
           tc_fence_after();
           const int b = i & 1;
-          const uint32_t qa = smem_u32(sQ + t * Cfg::TILE_BYTES);
-          const uint32_t ka = smem_u32(sK + ((kbase + m) % NS) * Cfg::TILE_BYTES) + (i & 1) * 8192;
+          const uint64_t qd = make_smem_desc(smem_u32(sQ + t * Cfg::TILE_BYTES), 16, 1024);
+          const uint64_t kd = make_smem_desc(smem_u32(sK + ((kbase + m) % NS) * Cfg::TILE_BYTES) + (i & 1) * 8192, 16, 1024);
           const uint32_t d_tmem = tmem_base + t * 128 + b * 64;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
-            umma_ss(d_tmem, make_smem_desc(qa + off, 16, 1024), make_smem_desc(ka + off, 16, 1024), idesc_qk,
-                    kk != 0 ? 1u : 0u);
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint32_t off = ((kk / 4) * 16384 + (kk % 4) * 32) >> 4;
+              umma_ss(d_tmem, qd + off, kd + off, idesc_qk, kk != 0 ? 1u : 0u);
+            }
+            umma_commit(&s_full[t * 2 + b]);
           }
-          umma_commit(&s_full[t * 2 + b]);
+          __syncwarp();
         };
         auto issue_pv = [&](int t, int i) {
           const int m = i >> 1;
@@ -807,19 +825,25 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           mbar_wait(&p_full[t * 2 + b], scnt[t][b] & 1);
           ++scnt[t][b];
           tc_fence_after();
-          const uint32_t va = smem_u32(sV + ((vbase + m) % NS) * Cfg::TILE_BYTES) + (i & 1) * 8192;
+          const uint64_t vd = make_smem_desc(smem_u32(sV + ((vbase + m) % NS) * Cfg::TILE_BYTES) + (i & 1) * 8192, 16384, 1024);
           const uint32_t a_tmem = tmem_base + t * 128 + b * 64;
           const uint32_t d_tmem = tmem_base + 256 + t * D;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < A_BH / 16; ++kk)
-            umma_ts(d_tmem, a_tmem + kk * 8, make_smem_desc(va + kk * 2048, 16384, 1024), idesc_pv,
-                    (i > 0 || kk != 0) ? 1u : 0u);
-          umma_commit(&o_done[t]);
+            for (int kk = 0; kk < A_BH / 16; ++kk)
+              umma_ts(d_tmem, a_tmem + kk * 8, vd + (uint64_t)(kk * 128), idesc_pv, (i > 0 || kk != 0) ? 1u : 0u);
+            umma_commit(&o_done[t]);
+          }
+          __syncwarp();
         };
 
         for (int t = 0; t < 2; ++t)
           if (w.n[t] > 0) issue_qk(t, 0);
-        if (nmax == 1) umma_commit(&k_empty[kbase % NS]);
+        auto commit = [&](uint64_t* bar) {
+          if (elect_one()) umma_commit(bar);
+          __syncwarp();
+        };
+        if (nmax == 1) commit(&k_empty[kbase % NS]);
         for (int i = 0; i < nmax; ++i) {
           const int s = i + 1;
           // queue the next step's QK^T of both tiles first (they need no softmax result), so the
@@ -827,10 +851,10 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           if (s < w.n[0]) issue_qk(0, s);
           if (s < w.n[1]) issue_qk(1, s);
           if (s < nmax && ((s & 1) == 1 || s == nmax - 1))
-            umma_commit(&k_empty[(kbase + (s >> 1)) % NS]);   // last QK on this K tile has been issued
+            commit(&k_empty[(kbase + (s >> 1)) % NS]);   // last QK on this K tile has been issued
           if (i < w.n[0]) issue_pv(0, i);
           if (i < w.n[1]) issue_pv(1, i);
-          if ((i & 1) == 1 || i == nmax - 1) umma_commit(&v_empty[(vbase + (i >> 1)) % NS]);
+          if ((i & 1) == 1 || i == nmax - 1) commit(&v_empty[(vbase + (i >> 1)) % NS]);
         }
         kbase += ntile;
         vbase += ntile;

@@ -115,8 +115,11 @@ __global__ void __launch_bounds__(G_THREADS, 1)
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
+    // warp-uniform control flow, one elected lane issues: descriptors stay in uniform registers
+    {
       constexpr uint32_t idesc = make_idesc_bf16(G_BM, G_BN, 0, 0);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -128,18 +131,22 @@ __global__ void __launch_bounds__(G_THREADS, 1)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * G_A_BYTES), 16, 1024);
-          const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * G_B_BYTES), 16, 1024);
+          const uint64_t adesc = adesc0 + (uint64_t)((stage * G_A_BYTES) >> 4);
+          const uint64_t bdesc = bdesc0 + (uint64_t)((stage * G_B_BYTES) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < G_BK / 16; ++kk)
-            umma_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+            for (int kk = 0; kk < G_BK / 16; ++kk)
+              umma_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+            umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          }
+          __syncwarp();
           if (++stage == G_STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&acc_full[as]);
+        if (elect_one()) umma_commit(&acc_full[as]);
+        __syncwarp();
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
