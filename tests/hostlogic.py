@@ -41,6 +41,21 @@ def _attention_fwd(q, k, v, *, causal, scale=None, layout="bshd", return_lse=Fal
     return (o, lse) if return_lse else o
 
 
+def _seg_pos(sq, q_seg_len, q_seg_pos):
+    if q_seg_len is not None and q_seg_pos is not None:
+        return torch.cat([torch.arange(q_seg_len) + q_seg_pos[i] for i in range(sq // q_seg_len)])
+    if q_seg_pos is not None:
+        return torch.arange(sq) + q_seg_pos[0]
+    return None
+
+
+def _attention_bwd(d_out, q, k, v, out, lse, *, causal, scale=None, q_seg_len=None, q_seg_pos=None, kv_pos0=0):
+    with torch.enable_grad():      # the oracle differentiates by autograd; this runs inside an autograd backward
+        dq, dk, dv = O.attention_grads(q, k, v, d_out, causal=causal, scale=scale,
+                                       q_pos=_seg_pos(q.shape[1], q_seg_len, q_seg_pos), kv_pos=torch.arange(k.shape[1]) + kv_pos0)
+    return _bf(dq), _bf(dk), _bf(dv)
+
+
 def _rmsnorm(x, weight, eps=1e-6, residual=None):
     if residual is None:
         return O.rmsnorm(x, weight, eps)
@@ -101,6 +116,7 @@ def _row_scatter_zero(x, idx, n_rows_out):
 
 SUBSTITUTES = {
     "attention_fwd": _attention_fwd,
+    "attention_bwd": _attention_bwd,
     "rmsnorm": _rmsnorm,
     "layernorm": lambda x, w, b, eps=1e-6: O.layernorm(x, w, b, eps),
     "rope_table": _rope_table,

@@ -81,3 +81,42 @@ def test_context_parallel_matches_single_device(lib_built, world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     mp.spawn(_worker, args=(world, _free_port()), nprocs=world, join=True)
+
+
+def _bwd_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from long_vita_b200 import cp as CP
+        from oracle import ops as O
+
+        hq, hkv, d = 10, 2, 128
+        S = 2 * world * 256
+        ctx = CP.CPContext(dist.group.WORLD, S, hq, hkv, d, dev, fused_qkv=False)
+        own = CP.zigzag_index(S, world, rank)
+        for step in range(2):                                   # two steps: both buffer parities, epochs continue
+            g = torch.Generator().manual_seed(500 + step)       # same tensors on every rank
+            q = torch.randn(S, hq, d, generator=g).to(torch.bfloat16)
+            k = torch.randn(S, hkv, d, generator=g).to(torch.bfloat16)
+            v = torch.randn(S, hkv, d, generator=g).to(torch.bfloat16)
+            d_out = torch.randn(S, hq * d, generator=g).to(torch.bfloat16)
+            ql, kl, vl = (t[own].to(dev).requires_grad_(True) for t in (q, k, v))
+            out = CP.cp_attention(ql, kl, vl, ctx)
+            out.backward(d_out[own].to(dev))
+            dq, dk, dv = O.attention_grads(q[None], k[None], v[None], d_out.view(1, S, hq, d), causal=True)
+            for name, got, ref in (("dq", ql.grad, dq[0][own]), ("dk", kl.grad, dk[0][own]), ("dv", vl.grad, dv[0][own])):
+                e = _rel(got, ref)
+                # single-GPU backward tolerance (tests/test_gpu_attention_bwd.py) plus one bf16 rounding of the
+                # partial dK/dV before the reduce-scatter
+                assert e < 8e-3, (rank, step, name, e)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_context_parallel_backward_matches_single_device(lib_built, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    mp.spawn(_bwd_worker, args=(world, _free_port()), nprocs=world, join=True)
