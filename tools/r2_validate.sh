@@ -1,0 +1,27 @@
+#!/bin/bash
+# First GPU call of round 2: validate the r2-prep kernel changes (warp-uniform MMA issue) on ONE GPU.
+#   gpurun --timeout 1500 -- 'bash tools/r2_validate.sh'
+# Every step runs under its own timeout; a hang in a new kernel costs at most that step.
+mkdir -p gpurun_out
+T="timeout -k 5"
+$T 120 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { tail -20 gpurun_out/build.log; exit 1; }
+# 1. smallest possible smoke of each touched kernel first (fast fail)
+$T 90 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "== smoke exit $?"; tail -n 3 gpurun_out/smoke.log
+# 2. parity suites of the touched kernels
+$T 300 python -m pytest tests/test_gpu_attention.py tests/test_gpu_gemm.py tests/test_gpu_attention_bwd.py -m gpu -q -x --timeout 90 --timeout-method=thread > gpurun_out/test_kernels.log 2>&1
+echo "== kernel parity exit $?"; tail -n 6 gpurun_out/test_kernels.log
+$T 400 python -m pytest tests -m gpu -q -x --timeout 120 --timeout-method=thread --deselect tests/test_gpu_cp.py > gpurun_out/test_all.log 2>&1
+echo "== all 1-GPU tests exit $?"; tail -n 6 gpurun_out/test_all.log
+# 3. speed: attention v1 / v2 / v3, GEMM, backward
+for V in 1 2 3; do
+  LV_ATTN_VERSION=$V $T 200 python tools/bench_kernels.py --only attn --quick --out gpurun_out/r2_attn_v$V.json > gpurun_out/r2_attn_v$V.log 2>&1
+  echo "== attn v$V exit $?"; cut -c1-170 gpurun_out/r2_attn_v$V.log | tail -n 8
+done
+$T 200 python tools/bench_kernels.py --only gemm --quick --out gpurun_out/r2_gemm.json > gpurun_out/r2_gemm.log 2>&1
+echo "== gemm exit $?"; cut -c1-170 gpurun_out/r2_gemm.log | tail -n 8
+$T 200 python tools/bench_bwd.py > gpurun_out/r2_bwd.log 2>&1
+echo "== bwd exit $?"; tail -n 6 gpurun_out/r2_bwd.log
+# 4. the headline
+$T 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
+echo "== bench exit $?"; cut -c1-600 gpurun_out/r2_bench_n1.json
