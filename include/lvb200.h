@@ -139,7 +139,8 @@ typedef struct lv_cp_params {
   void* my_ready;            /* local base of the same array */
   void* k_full;              /* bf16 [S, hkv*d] staging (local) */
   void* v_full;
-  void* blk_flags;           /* uint32 [S/128], zero-initialised once */
+  void* blk_flags;           /* uint32 [S/128], zero-initialised once; private to the kernel (it counts
+                              * staged 32-token units: 4 * (epoch + 1) when block b of this epoch is whole) */
 } lv_cp_params;
 
 int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv_stream_t stream);

@@ -93,6 +93,19 @@ __device__ __forceinline__ uint4 ld_peer_v4(const void* p) {
   return v;
 }
 
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Staging granularity: a 128-token key block is pulled as CP_SUB units of 32 tokens by different copier
+// warps, and blk_flags[b] COUNTS completed units (it reaches CP_SUB * (epoch + 1) when block b of this
+// epoch is whole).  With one unit per warp-visit and 8 x 16 B loads in flight per lane, a rank with few
+// blocks (short sequences) still keeps every copier warp of the grid and ~1.2 MB of NVLink reads in
+// flight; the first version moved one whole block per warp with 4 loads in flight and needed ~0.5 ms per
+// layer at 18K tokens / 8 ranks, all of it exposed.
+constexpr int CP_SUB = 4;
+constexpr int CP_UNIT_ROWS = A_BN / CP_SUB;
+
 __device__ __forceinline__ void cp_copier(const CpKParams& cpp, int warp, int lane) {
       const int cw = blockIdx.x * 2 + (warp - 2);          // copier index
       const int ncw = gridDim.x * 2;
@@ -105,8 +118,10 @@ __device__ __forceinline__ void cp_copier(const CpKParams& cpp, int warp, int la
       uint32_t seen = 1u << cpp.rank;                      // peers whose ready flag has been observed
       const int vec_per_row = cpp.kv_row_elems / 4;        // 16-byte vectors in one K|V row pair
       const int vec_per_half = cpp.kv_row_elems / 8;
-      for (int b = cw; b < cpp.nblk_needed; b += ncw) {
-        const int tok0 = b * A_BN;
+      const int n_units = cpp.nblk_needed * CP_SUB;
+      for (int u = cw; u < n_units; u += ncw) {
+        const int b = u / CP_SUB;
+        const int tok0 = b * A_BN + (u - b * CP_SUB) * CP_UNIT_ROWS;
         const int chunk = tok0 / cpp.chunk;
         const int owner = chunk < cpp.cp ? chunk : 2 * cpp.cp - 1 - chunk;
         const int lrow0 = (chunk < cpp.cp ? 0 : cpp.chunk) + (tok0 - chunk * cpp.chunk);
@@ -118,28 +133,55 @@ __device__ __forceinline__ void cp_copier(const CpKParams& cpp, int warp, int la
           seen |= 1u << owner;
         }
         const __nv_bfloat16* src = cpp.peer_kv[owner] + (long long)lrow0 * cpp.peer_tok_stride;
-        const int total = A_BN * vec_per_row;
-        for (int i0 = 0; i0 < total; i0 += 32 * 4) {
-          uint4 v[4];
+        if (vec_per_row == 256) {
+          // K|V row pair = 4 KB (8 kv heads x 128): one row per warp pass, 8 loads in flight per lane,
+          // vectors 0..127 of the row are K, 128..255 are V
+          const __nv_bfloat16* s_lane = src + lane * 8;
+          __nv_bfloat16* dk = cpp.k_full + (long long)tok0 * cpp.kv_row_elems + lane * 8;
+          __nv_bfloat16* dv = cpp.v_full + (long long)tok0 * cpp.kv_row_elems + lane * 8;
+#pragma unroll 1
+          for (int row = 0; row < CP_UNIT_ROWS; ++row) {
+            uint4 v[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * 32 + lane;
-            const int row = i / vec_per_row, col = i - row * vec_per_row;
-            v[u] = ld_peer_v4(src + (long long)row * cpp.peer_tok_stride + col * 8);
+            for (int i = 0; i < 8; ++i) v[i] = ld_peer_v4(s_lane + i * 256);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              *reinterpret_cast<uint4*>(dk + i * 256) = v[i];
+              *reinterpret_cast<uint4*>(dv + i * 256) = v[4 + i];
+            }
+            s_lane += cpp.peer_tok_stride;
+            dk += cpp.kv_row_elems;
+            dv += cpp.kv_row_elems;
           }
+        } else {
+          const int total = CP_UNIT_ROWS * vec_per_row;
+          for (int i0 = 0; i0 < total; i0 += 32 * 4) {
+            uint4 v[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * 32 + lane;
-            const int row = i / vec_per_row, col = i - row * vec_per_row;
-            __nv_bfloat16* dst = col < vec_per_half
-                                     ? cpp.k_full + (long long)(tok0 + row) * cpp.kv_row_elems + col * 8
-                                     : cpp.v_full + (long long)(tok0 + row) * cpp.kv_row_elems + (col - vec_per_half) * 8;
-            *reinterpret_cast<uint4*>(dst) = v[u];
+            for (int k = 0; k < 4; ++k) {
+              const int i = i0 + k * 32 + lane;
+              const int row = i / vec_per_row, col = i - row * vec_per_row;
+              if (i < total) v[k] = ld_peer_v4(src + (long long)row * cpp.peer_tok_stride + col * 8);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int i = i0 + k * 32 + lane;
+              const int row = i / vec_per_row, col = i - row * vec_per_row;
+              if (i < total) {
+                __nv_bfloat16* dst = col < vec_per_half
+                                         ? cpp.k_full + (long long)(tok0 + row) * cpp.kv_row_elems + col * 8
+                                         : cpp.v_full + (long long)(tok0 + row) * cpp.kv_row_elems + (col - vec_per_half) * 8;
+                *reinterpret_cast<uint4*>(dst) = v[k];
+              }
+            }
           }
         }
+        // the staged rows are read by TMA (async proxy): order this lane's generic-proxy stores before the
+        // async proxy on the writer side as well (the producer fences again after its acquire)
+        fence_proxy_async_all();
         __threadfence();
         __syncwarp();
-        if (lane == 0) st_release_gpu(cpp.blk_flags + b, cpp.epoch1);
+        if (lane == 0) red_release_gpu_add(cpp.blk_flags + b, 1u);
       }
       if (cw == 0) {
         // do not retire before every peer has entered this epoch: a peer's flag for epoch e+1 then
@@ -310,7 +352,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         }
         for (int j = 0; j < nmax; ++j) {
           if (CP && j >= ready_upto) {
-            while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1) {
+            while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1 * CP_SUB) {
             }
             ready_upto = j + 1;
             fence_proxy_async_all();   // copier warps wrote the staging rows through the generic proxy
@@ -749,7 +791,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         }
         for (int j = 0; j < ntile; ++j) {
           if (CP && j >= ready_upto) {
-            while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1) {
+            while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1 * CP_SUB) {
             }
             ready_upto = j + 1;
             fence_proxy_async_all();
