@@ -45,6 +45,7 @@ struct AttnKParams {
   int n_qblk;      // ceil(sq / 256)
   int n_items;     // batch * hq * n_qblk
   int block_major; // 1: order work items (q-block, kv-head, head) - global longest-first; 0: (kv-head, q-block, head)
+  int poly_exp;    // 1: every 4th exponential of the softmax runs on the FMA pipe (polynomial), the rest on MUFU
   float* lse;
 };
 
@@ -90,6 +91,51 @@ __device__ __forceinline__ uint4 ld_peer_v4(const void* p) {
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(p)
                : "memory");
+  return v;
+}
+
+// 2^x on the FMA pipe (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic minimax for 2^f
+// (max relative error 7.5e-5, tools/exp2_poly.py - 50x below the bf16 rounding P gets anyway), exponent
+// add through the low mantissa bits of the magic-number sum.  x is clamped to >= -125 so the result
+// stays a normal number (a masked -inf score becomes 2^-125 ~ 2e-38 instead of 0: invisible in l and P V).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;            // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.055171321f, f, 0.24261054f);
+  p = fmaf(p, f, 0.69326099f);
+  p = fmaf(p, f, 0.99992811f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// One 32-column chunk of a score row: P = 2^(S * scale_log2 - m), four partial row sums, bf16 pack.
+// POLY: every 4th exponential is evaluated on the FMA pipe (ex2_poly), relieving the MUFU pipe that both
+// softmax warpgroups share (16 ex2 / clk / SM = as many cycles as the two MMAs of a step at d = 128).
+template <bool POLY>
+__device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&sc)[32], float scale_log2, float neg_m, float& l0,
+                                                  float& l1, float& l2, float& l3, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float p0 = ex2(fmaf(__uint_as_float(sc[i + 0]), scale_log2, neg_m));
+    const float p1 = ex2(fmaf(__uint_as_float(sc[i + 1]), scale_log2, neg_m));
+    const float p2 = ex2(fmaf(__uint_as_float(sc[i + 2]), scale_log2, neg_m));
+    const float x3 = fmaf(__uint_as_float(sc[i + 3]), scale_log2, neg_m);
+    const float p3 = POLY ? ex2_poly(x3) : ex2(x3);
+    l0 += p0;
+    l1 += p1;
+    l2 += p2;
+    l3 += p3;
+    pk[i / 2] = pack_bf16(p0, p1);
+    pk[i / 2 + 1] = pack_bf16(p2, p3);
+  }
+}
+
+// LV_ATTN_POLY=1: softmax exponentials split 3:1 between MUFU (ex2.approx) and the FMA pipe.
+static int attn_poly_exp() {
+  static const int v = [] {
+    const char* e = getenv("LV_ATTN_POLY");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+  }();
   return v;
 }
 
@@ -574,19 +620,10 @@ __global__ void __launch_bounds__(A_THREADS, 1)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float p0 = ex2(fmaf(__uint_as_float(s[c][i + 0]), p.scale_log2, neg_m));
-            const float p1 = ex2(fmaf(__uint_as_float(s[c][i + 1]), p.scale_log2, neg_m));
-            const float p2 = ex2(fmaf(__uint_as_float(s[c][i + 2]), p.scale_log2, neg_m));
-            const float p3 = ex2(fmaf(__uint_as_float(s[c][i + 3]), p.scale_log2, neg_m));
-            l0 += p0;
-            l1 += p1;
-            l2 += p2;
-            l3 += p3;
-            pk[i / 2] = pack_bf16(p0, p1);
-            pk[i / 2 + 1] = pack_bf16(p2, p3);
-          }
+          if (p.poly_exp)
+            softmax_exp_chunk<true>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
+          else
+            softmax_exp_chunk<false>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
           tmem_st16(tS + c * 16, pk);
           if (QH) {
             tmem_wait_st();          // (also covers the lazy O rescale before the first quarter)
@@ -977,19 +1014,10 @@ __global__ void __launch_bounds__(A_THREADS, 1)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t pk[16];
-#pragma unroll
-          for (int k = 0; k < 32; k += 4) {
-            const float p0 = ex2(fmaf(__uint_as_float(s[c][k + 0]), p.scale_log2, neg_m));
-            const float p1 = ex2(fmaf(__uint_as_float(s[c][k + 1]), p.scale_log2, neg_m));
-            const float p2 = ex2(fmaf(__uint_as_float(s[c][k + 2]), p.scale_log2, neg_m));
-            const float p3 = ex2(fmaf(__uint_as_float(s[c][k + 3]), p.scale_log2, neg_m));
-            l0 += p0;
-            l1 += p1;
-            l2 += p2;
-            l3 += p3;
-            pk[k / 2] = pack_bf16(p0, p1);
-            pk[k / 2 + 1] = pack_bf16(p2, p3);
-          }
+          if (p.poly_exp)
+            softmax_exp_chunk<true>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
+          else
+            softmax_exp_chunk<false>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
           tmem_st16(tS + b * 64 + c * 16, pk);
         }
         l += (l0 + l1) + (l2 + l3);
@@ -1114,6 +1142,7 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
   // all kv heads' K and V fit comfortably in the 126 MB L2 -> global longest-first order
   p.block_major = (a->causal && a->sk * a->hkv * a->d * 4 <= (64ll << 20)) ? 1 : 0;
   p.lse = a->lse;
+  p.poly_exp = attn_poly_exp();
   static bool attr_set = false;
   if (!attr_set) {
     if constexpr (VER == 2) {

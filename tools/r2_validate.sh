@@ -18,6 +18,13 @@ for V in 1 2 3; do
   LV_ATTN_VERSION=$V $T 200 python tools/bench_kernels.py --only attn --quick --out gpurun_out/r2_attn_v$V.json > gpurun_out/r2_attn_v$V.log 2>&1
   echo "== attn v$V exit $?"; cut -c1-170 gpurun_out/r2_attn_v$V.log | tail -n 8
 done
+# 3b. polynomial exp2 on the FMA pipe for every 4th softmax element (LV_ATTN_POLY=1): parity, then speed
+LV_ATTN_POLY=1 $T 200 python -m pytest tests/test_gpu_attention.py -m gpu -q -x --timeout 90 --timeout-method=thread > gpurun_out/test_attn_poly.log 2>&1
+echo "== attention parity with poly exp2: exit $?"; tail -n 4 gpurun_out/test_attn_poly.log
+for V in 1 2; do
+  LV_ATTN_POLY=1 LV_ATTN_VERSION=$V $T 200 python tools/bench_kernels.py --only attn --quick --out gpurun_out/r2_attn_poly_v$V.json > gpurun_out/r2_attn_poly_v$V.log 2>&1
+  echo "== attn poly v$V exit $?"; cut -c1-170 gpurun_out/r2_attn_poly_v$V.log | tail -n 8
+done
 $T 200 python tools/bench_kernels.py --only gemm --quick --out gpurun_out/r2_gemm.json > gpurun_out/r2_gemm.log 2>&1
 echo "== gemm exit $?"; cut -c1-170 gpurun_out/r2_gemm.log | tail -n 8
 $T 200 python tools/bench_bwd.py > gpurun_out/r2_bwd.log 2>&1
