@@ -451,6 +451,57 @@ def masked_linear_dgrad(grad_out: torch.Tensor, weight: torch.Tensor, logit_mask
     return row_scatter_zero(gi, idx, s).view(s, 1, -1)
 
 
+def masked_linear_wgrad(grad_out: torch.Tensor, h: torch.Tensor, logit_mask: torch.Tensor):
+    """dW of masked_linear: dY^T . masked_select(h) -> [vocab, c] (layers.py:451-456, 512-520: `grad_output.t()
+    .matmul(total_input)`).  Runs on the same tcgen05 GEMM with the contraction over the M selected rows: both
+    operands are transposed once ([vocab, M] and [c, M]; M is the number of answer tokens) and M is zero-padded
+    to a multiple of 8 (the GEMM's K granularity)."""
+    _need_cuda_bf16(grad_out, h)
+    s, b, c = h.shape
+    m = grad_out.shape[0]
+    vocab = grad_out.shape[-1]
+    if m == 0:
+        return torch.zeros((vocab, c), dtype=torch.bfloat16, device=h.device)
+    idx = logit_mask.reshape(-1).nonzero().view(-1)
+    sel = row_gather(h.reshape(s, c), idx)                              # [M, c]
+    mp = (m + 7) // 8 * 8
+    gt = torch.zeros((vocab, mp), dtype=torch.bfloat16, device=h.device)
+    gt[:, :m] = grad_out.reshape(m, vocab).t()
+    st = torch.zeros((c, mp), dtype=torch.bfloat16, device=h.device)
+    st[:, :m] = sel.t()
+    return linear(gt, st)                                               # [vocab, c]
+
+
+class _MaskedLinearFn(torch.autograd.Function):
+    """LinearWithGradAccumulationAndAsyncCommunication with `logit_mask` (layers.py:371-456) for tp = 1,
+    no sequence parallelism, no gradient-accumulation fusion: forward = gather + GEMM, backward =
+    dX = masked_scatter(zeros, dY W) and (when the weight trains) dW = dY^T sel."""
+
+    @staticmethod
+    def forward(ctx, h, weight, logit_mask):
+        ctx.save_for_backward(h, weight, logit_mask)
+        return masked_linear(h, weight, logit_mask)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        h, weight, logit_mask = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        gh = gw = None
+        if ctx.needs_input_grad[0]:
+            if grad_out.shape[0] == 0:
+                gh = torch.zeros_like(h)
+            else:
+                gh = masked_linear_dgrad(grad_out, weight, logit_mask)
+        if ctx.needs_input_grad[1]:
+            gw = masked_linear_wgrad(grad_out, h, logit_mask)
+        return gh, gw, None
+
+
+def masked_linear_autograd(h: torch.Tensor, weight: torch.Tensor, logit_mask: torch.Tensor):
+    """Differentiable logit-masked LM head."""
+    return _MaskedLinearFn.apply(h, weight, logit_mask)
+
+
 def patch_embed(images: torch.Tensor, w_pad: torch.Tensor, bias: Optional[torch.Tensor], cls: torch.Tensor,
                 pos: torch.Tensor, patch: int):
     """images [n,3,S,S] -> [n, 1 + (S/patch)^2, C] (conv-as-GEMM + cls + position embedding).

@@ -146,3 +146,24 @@ def test_whole_layer_spec_module_matches_oracle_decoder_layer(lib_built):
     cos, sin = O.rope_tables(torch.arange(s), inv, torch.bfloat16)
     ref = OM.decoder_layer(cfg, OM.cast_weights(w, torch.float32), 0, x[:, 0].float(), cos.float(), sin.float())
     assert rel_fro(out[:, 0], ref) < 4e-3, rel_fro(out[:, 0], ref)
+
+
+def test_masked_lm_head_autograd(lib_built):
+    """a12 backward on the kernels: dX scatter and dW = dY^T sel through the transposed-operand GEMM (K = M
+    padded to 8)."""
+    from long_vita_b200 import ops
+
+    g = seeded(12)
+    s, c, vocab = 300, 640, 2048
+    h = randn_bf16((s, 1, c), g)
+    w = randn_bf16((vocab, c), g, scale=0.05)
+    mask = torch.zeros(1, s, dtype=torch.bool)
+    mask[0, [5, 6, 77, 150, 299]] = True
+    dy = randn_bf16((5, 1, vocab), g)
+    hg, wg = h.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    out = ops.masked_linear_autograd(hg, wg, mask.cuda())
+    out.backward(dy.cuda())
+    ref_out = O.masked_linear_fwd(h.float(), w.float(), mask)
+    gx, gw = O.masked_linear_bwd(dy.float(), h.float(), w.float(), mask)
+    assert rel_fro(out, ref_out) < 4e-3
+    assert rel_fro(hg.grad, gx) < 4e-3 and rel_fro(wg.grad, gw) < 4e-3

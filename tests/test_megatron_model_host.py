@@ -465,3 +465,29 @@ def test_forward_glue_equals_the_references_own_gptvl_forward(tiny, model):
                 assert got.shape == want.shape and torch.equal(got, want), sorted(kw)
     finally:
         dist.destroy_process_group()
+
+
+def test_masked_lm_head_autograd_matches_reference_formulas():
+    """a12: dX = masked_scatter(zeros, dY W), dW = dY^T sel (layers.py:443-456) through the product's own
+    composition (gather / padded transposes / scatter), kernels replaced by the oracle."""
+    from oracle import ops as O
+
+    g = torch.Generator().manual_seed(8)
+    s, c, vocab = 40, 64, 96
+    h = torch.randn(s, 1, c, generator=g).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(vocab, c, generator=g) * 0.1).to(torch.bfloat16).requires_grad_(True)
+    mask = torch.zeros(1, s, dtype=torch.bool)
+    mask[0, [3, 4, 17, 30, 39]] = True                          # M = 5: exercises the zero padding to 8
+    dy = torch.randn(5, 1, vocab, generator=g).to(torch.bfloat16)
+    with oracle_ops() as ops:
+        out = ops.masked_linear_autograd(h, w, mask)
+        out.backward(dy)
+        empty = ops.masked_linear_autograd(h.detach().requires_grad_(True), w.detach(), torch.zeros(1, s, dtype=torch.bool))
+        assert empty.shape == (0, 1, vocab)
+    ref_out = O.masked_linear_fwd(h.detach().float(), w.detach().float(), mask)
+    gx, gw = O.masked_linear_bwd(dy.float(), h.detach().float(), w.detach().float(), mask)
+    assert rel_fro(out, ref_out) < 5e-3
+    assert rel_fro(h.grad, gx) < 5e-3 and rel_fro(w.grad, gw) < 5e-3
+    unmasked = torch.ones(s, dtype=torch.bool)
+    unmasked[[3, 4, 17, 30, 39]] = False
+    assert not h.grad[unmasked].any()                           # rows outside the mask get exactly zero
