@@ -211,6 +211,61 @@ def attention(q, k, v, *, causal: bool, scale: Optional[float] = None):
     return _AttentionFn.apply(q, k, v, causal, scale)
 
 
+def _sm_count(device) -> int:
+    return torch.cuda.get_device_properties(device).multi_processor_count if torch.cuda.is_available() else 148
+
+
+def attention_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, length: int, *,
+                     scale: Optional[float] = None, n_splits: Optional[int] = None, return_lse: bool = False):
+    """One new token against a K/V cache (the reference has no such path - it re-prefills
+    every generated token, long_vita_megatron/inference/text_generation/generation.py:127-135).
+
+    q [hq, d]; k_cache / v_cache [>= length, hkv, d] (post-RoPE rows of the previous tokens, the new token's
+    row already appended); returns out [hq, d] (and lse [hq] fp32, natural log - what a context-parallel
+    combine across cache shards needs).
+
+    HBM-bound (every K/V row is read once), so the job is to put all SMs on the cache: the G = hq / hkv query
+    heads of a kv group become G query ROWS of one head (they share K/V), and the key range is cut into
+    `n_splits` chunks that run as the batch dimension of the ordinary fused kernel (`lv_attn_fwd`,
+    non-causal, with LSE); the partial results are merged by their log-sum-exp weights (flash-decoding).
+    A ragged last chunk is a second launch with sk = remainder."""
+    _need_cuda_bf16(q, k_cache, v_cache)
+    hq, d = q.shape
+    hkv = k_cache.shape[1]
+    G = hq // hkv
+    if length <= 0 or length > k_cache.shape[0]:
+        raise ValueError(f"attention_decode: length {length} outside the cache (capacity {k_cache.shape[0]})")
+    if n_splits is None:
+        n_splits = max(1, _sm_count(q.device) // hkv)
+    per = -(-length // n_splits)
+    chunk = max(128, (per + 127) // 128 * 128)                             # keys per split, whole 128-key tiles
+    n_full, rem = divmod(length, chunk)
+    qp = q.view(hkv, G, d).transpose(0, 1)                                 # [G rows, hkv heads, d]
+    outs, lses = [], []
+    if n_full:
+        qb = qp.unsqueeze(0).expand(n_full, G, hkv, d).contiguous()
+        kb = k_cache[: n_full * chunk].view(n_full, chunk, hkv, d)
+        vb = v_cache[: n_full * chunk].view(n_full, chunk, hkv, d)
+        o, l = attention_fwd(qb, kb, vb, causal=False, scale=scale, return_lse=True)   # [n, G, hkv, d], [n, hkv, G]
+        outs.append(o)
+        lses.append(l)
+    if rem:
+        o, l = attention_fwd(qp.unsqueeze(0).contiguous(), k_cache[n_full * chunk : length].unsqueeze(0),
+                             v_cache[n_full * chunk : length].unsqueeze(0), causal=False, scale=scale, return_lse=True)
+        outs.append(o)
+        lses.append(l)
+    o = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)              # [n, G, hkv, d]
+    l = lses[0] if len(lses) == 1 else torch.cat(lses, dim=0)              # [n, hkv, G]
+    lse = torch.logsumexp(l, dim=0)                                        # [hkv, G]
+    if o.shape[0] == 1:
+        out = o[0]
+    else:
+        wgt = torch.exp(l - lse.unsqueeze(0)).permute(0, 2, 1).unsqueeze(-1)   # [n, G, hkv, 1]
+        out = (o.float() * wgt).sum(dim=0).to(torch.bfloat16)
+    out = out.transpose(0, 1).reshape(hq, d)                               # head h = kvh * G + g
+    return (out, lse.reshape(hq)) if return_lse else out
+
+
 # ------------------------------------------------------------------------------------------------
 # token-wise operators
 # ------------------------------------------------------------------------------------------------
