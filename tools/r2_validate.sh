@@ -13,6 +13,9 @@ $T 300 python -m pytest tests/test_gpu_attention.py tests/test_gpu_gemm.py tests
 echo "== kernel parity exit $?"; tail -n 6 gpurun_out/test_kernels.log
 $T 400 python -m pytest tests -m gpu -q -x --timeout 120 --timeout-method=thread --deselect tests/test_gpu_cp.py > gpurun_out/test_all.log 2>&1
 echo "== all 1-GPU tests exit $?"; tail -n 6 gpurun_out/test_all.log
+# 2b. the double-buffered-S kernel (v2) shares the new issue path: parity before it is timed
+LV_ATTN_VERSION=2 $T 200 python -m pytest tests/test_gpu_attention.py -m gpu -q -x --timeout 90 --timeout-method=thread > gpurun_out/test_attn_v2.log 2>&1
+echo "== attention parity v2: exit $?"; tail -n 4 gpurun_out/test_attn_v2.log
 # 3. speed: attention v1 / v2 / v3, GEMM, backward
 for V in 1 2 3; do
   LV_ATTN_VERSION=$V $T 200 python tools/bench_kernels.py --only attn --quick --out gpurun_out/r2_attn_v$V.json > gpurun_out/r2_attn_v$V.log 2>&1
