@@ -35,3 +35,6 @@ echo "== bwd exit $?"; tail -n 6 gpurun_out/r2_bwd.log
 # 4. the headline
 $T 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
 echo "== bench exit $?"; cut -c1-600 gpurun_out/r2_bench_n1.json
+# 5. K/V-cache decode (8f-2): ms per token at the 18K context next to the re-prefill the reference does
+$T 300 python tools/bench_decode.py --tokens 16 > gpurun_out/r2_decode.json 2> gpurun_out/r2_decode.err
+echo "== decode exit $?"; tail -2 gpurun_out/r2_decode.err; cut -c1-600 gpurun_out/r2_decode.json
