@@ -30,6 +30,8 @@ for V in 1 2; do
 done
 $T 200 python tools/bench_kernels.py --only gemm --quick --out gpurun_out/r2_gemm.json > gpurun_out/r2_gemm.log 2>&1
 echo "== gemm exit $?"; cut -c1-170 gpurun_out/r2_gemm.log | tail -n 8
+LV_GEMV=0 $T 200 python tools/bench_kernels.py --only gemm --quick --out gpurun_out/r2_gemm_nogemv.json > gpurun_out/r2_gemm_nogemv.log 2>&1
+echo "== gemm (LM head through the tensor-core kernel, LV_GEMV=0) exit $?"; grep -i "lm\|152064" gpurun_out/r2_gemm_nogemv.log | cut -c1-170 | tail -n 3
 $T 200 python tools/bench_bwd.py > gpurun_out/r2_bwd.log 2>&1
 echo "== bwd exit $?"; tail -n 6 gpurun_out/r2_bwd.log
 # 4. the headline
