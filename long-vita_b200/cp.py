@@ -320,6 +320,8 @@ class ContextParallelRunner:
         self.cp = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.ctx: Optional[CPContext] = None
+        self.cache = None          # this rank's K/V cache shard after forward(..., use_cache=True)
+        self.total_len = 0         # tokens in the whole (sharded) cache
 
     def _context(self, S: int, device) -> CPContext:
         cfg = self.model.config
@@ -328,7 +330,7 @@ class ContextParallelRunner:
         return self.ctx
 
     def forward(self, input_ids: torch.Tensor, images: Optional[torch.Tensor], image_indices: Optional[torch.Tensor],
-                gather_logits: bool = True) -> torch.Tensor:
+                gather_logits: bool = True, use_cache: bool = False, max_new_tokens: int = 1024) -> torch.Tensor:
         """Every rank passes the FULL prompt (the reference broadcasts it, tasks/inference/module.py
         :340-356) and keeps its shard.  Returns the last-token logits [1, 1, vocab] on every rank."""
         from . import ops
@@ -346,9 +348,17 @@ class ContextParallelRunner:
                               sh.src_idx if feat is not None else None)
         cos, sin = ops.rope_table(sh.position_ids.to(torch.int64), m.inv_freq)
         T = x.shape[0]
+        self.cache = None
+        if use_cache:      # this rank's shard of the K/V cache: its T zig-zag rows + its share of the new tokens
+            from .kv_cache import KVCache
+
+            self.cache = KVCache(len(m.layers), T + -(-max_new_tokens // self.cp) + 1, cfg.num_key_value_heads, cfg.head_dim, dev)
+            self.total_len = S
         delta = None
-        for layer in m.layers:
-            x, delta = layer.forward_cp(x, delta, cos, sin, ctx)
+        for li, layer in enumerate(m.layers):
+            x, delta = layer.forward_cp(x, delta, cos, sin, ctx, self.cache, li)
+        if self.cache is not None:
+            self.cache.commit()
         h, _ = ops.rmsnorm(delta, m.norm_w, cfg.rms_norm_eps, residual=x)
         # logit mask: each rank projects its own last row; the globally-last token lives on rank 0
         # (chunk 2cp-1), generation.py:141-165
@@ -357,3 +367,36 @@ class ContextParallelRunner:
         if gather_logits:
             dist.broadcast(logits, src=dist.get_global_rank(self.group, 0), group=self.group)
         return logits
+
+    # -- incremental decoding over the sharded cache (SURVEY.md 8f-2 under context parallelism) --------------
+    def _merge(self, o_loc: torch.Tensor, lse_loc: torch.Tensor) -> torch.Tensor:
+        """Combine the ranks' partial attention results over their cache shards: out = sum_r w_r o_r with
+        w_r = exp(lse_r - logsumexp_r lse_r).  One all-gather of [hq, d + 1] floats (20 KB at 40 x 128)."""
+        hq, d = o_loc.shape
+        pack = torch.cat([o_loc.float(), lse_loc.view(hq, 1)], dim=1).contiguous()
+        allp = torch.empty((self.cp * hq, d + 1), dtype=torch.float32, device=pack.device)
+        dist.all_gather_into_tensor(allp, pack, group=self.group)
+        allp = allp.view(self.cp, hq, d + 1)
+        w = torch.softmax(allp[:, :, d], dim=0)                   # -inf (empty shard) -> weight 0
+        return (allp[:, :, :d] * w.unsqueeze(-1)).sum(dim=0).to(torch.bfloat16)
+
+    def decode(self, token: torch.Tensor) -> torch.Tensor:
+        """One generated token after forward(..., use_cache=True): every rank runs the token through the
+        (replicated) weights; attention reads only this rank's cache shard and the partial results are merged.
+        The new K/V row goes to rank `position % cp`.  Returns the logits [1, 1, vocab] (same on every rank)."""
+        from . import ops
+
+        m = self.model.model
+        cfg = self.model.config
+        assert self.cache is not None, "call forward(..., use_cache=True) first"
+        pos = self.total_len
+        owner = (pos % self.cp) == self.rank
+        x = ops.embed_scatter(token.view(1, 1), m.embed_tokens)
+        cos, sin = ops.rope_table(torch.tensor([pos], dtype=torch.int64, device=x.device), m.inv_freq)
+        delta = None
+        for li, layer in enumerate(m.layers):
+            x, delta = layer.forward(x, delta, cos, sin, {}, self.cache, li, shard_merge=self._merge, append=owner)
+        self.cache.commit()
+        self.total_len += 1
+        h, _ = ops.rmsnorm(delta, m.norm_w, cfg.rms_norm_eps, residual=x)
+        return ops.linear(h, self.model.lm_head).view(1, 1, -1)

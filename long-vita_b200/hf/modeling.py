@@ -134,7 +134,7 @@ class DecoderLayer:
         self.ln2 = w[p + "post_attention_layernorm.weight"]
 
     def forward(self, x: torch.Tensor, delta: Optional[torch.Tensor], cos, sin, attn_kwargs, cache=None,
-                layer_idx: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                layer_idx: int = 0, shard_merge=None, append: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
         """x [T, H] residual stream, `delta` the previous layer's MLP output not yet added
         (the add is fused into this layer's first RMSNorm).  Returns (x, delta).  With `cache` the new
         K/V rows are appended to it and attention runs over cache + new rows."""
@@ -153,6 +153,20 @@ class DecoderLayer:
         ops.rope(k, cos, sin, out=k)
         if cache is None:
             att = ops.attention_fwd(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), causal=True, **attn_kwargs)
+        elif T == 1 and shard_merge is not None:
+            # context-parallel decode: the cache is sharded over the ranks (any split of the keys works for a
+            # query that sees them all); this rank attends over its shard, `shard_merge` combines the ranks'
+            # (out, lse) pairs.  Only the rank that owns the new position appends its K/V row.
+            if append:
+                kc, vc, length = cache.append(layer_idx, k, v)
+            else:
+                kc, vc, length = cache.k[layer_idx], cache.v[layer_idx], len(cache)
+            if length > 0:
+                o_loc, lse_loc = ops.attention_decode(q[0], kc, vc, length, return_lse=True)
+            else:
+                o_loc = torch.zeros((hq, d), dtype=torch.bfloat16, device=x.device)
+                lse_loc = torch.full((hq,), float("-inf"), dtype=torch.float32, device=x.device)
+            att = shard_merge(o_loc, lse_loc)
         else:
             kc, vc, length = cache.append(layer_idx, k, v)
             if T == 1:
@@ -164,7 +178,8 @@ class DecoderLayer:
         a = ops.linear(h, self.w_gate_up, act="swiglu")
         return x, ops.linear(a, self.w_down)
 
-    def forward_cp(self, x: torch.Tensor, delta: Optional[torch.Tensor], cos, sin, ctx) -> Tuple[torch.Tensor, torch.Tensor]:
+    def forward_cp(self, x: torch.Tensor, delta: Optional[torch.Tensor], cos, sin, ctx, cache=None,
+                   layer_idx: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
         """The same layer on this rank's zig-zag shard (`ctx` is the rank's cp.CPContext): the QKV GEMM
         writes straight into the peer-mapped buffer, RoPE runs in place there, and the fused kernel
         pulls the other ranks' K/V itself (lv_attn_cp_fwd)."""
@@ -180,6 +195,8 @@ class DecoderLayer:
         k = qkv[:, hq * d : (hq + hkv) * d].view(T, hkv, d)
         ops.rope(q, cos, sin, out=q)
         ops.rope(k, cos, sin, out=k)
+        if cache is not None:      # this rank's zig-zag rows become its shard of the K/V cache
+            cache.append(layer_idx, k, qkv[:, (hq + hkv) * d :].view(T, hkv, d))
         o = ops.linear(ctx.attention(), self.wo)
         h, x = ops.rmsnorm(o, self.ln2, cfg.rms_norm_eps, residual=x)
         a = ops.linear(h, self.w_gate_up, act="swiglu")

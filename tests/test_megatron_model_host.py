@@ -491,3 +491,65 @@ def test_masked_lm_head_autograd_matches_reference_formulas():
     unmasked = torch.ones(s, dtype=torch.bool)
     unmasked[[3, 4, 17, 30, 39]] = False
     assert not h.grad[unmasked].any()                           # rows outside the mask get exactly zero
+
+
+def _cp_decode_worker(rank, world, port, tmp):
+    import os
+
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from long_vita_b200 import cp as CP
+        from long_vita_b200.hf.modeling import LongVITAForCausalLM
+        from long_vita_b200.synthetic import build_prompt
+
+        torch.set_num_threads(2)
+        cfg = LongVITAConfig.tiny(layers=2, vit_layers=1)
+        hf = synthetic_state_dict(cfg, seed=77, dtype=torch.bfloat16, perturb=True)
+        ids, idx = build_prompt(cfg, 1, n_text=20, pad_multiple=2 * world * 128)
+        S = ids.shape[1]
+        images = torch.randn(1, 3, 448, 448, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+        new = torch.randint(0, cfg.vocab_size, (3,), generator=torch.Generator().manual_seed(4))
+        with oracle_ops():
+            model = LongVITAForCausalLM(cfg, hf)
+            runner = CP.ContextParallelRunner(model, dist.group.WORLD)
+            runner.ctx = _GlooCPContext(S, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim)
+            first = runner.forward(ids, images, idx, use_cache=True, max_new_tokens=8)
+            assert len(runner.cache) == S // world and runner.total_len == S
+            steps = [runner.decode(new[i]) for i in range(3)]
+            # rows went round-robin to rank (S + i) % world
+            assert len(runner.cache) == S // world + sum(1 for i in range(3) if (S + i) % world == rank)
+        if rank == 0:
+            torch.save({"first": first, "steps": torch.cat(steps, dim=1)}, tmp)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_cache_decode_equals_full_forward(tiny, tmp_path):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    from long_vita_b200.hf.modeling import LongVITAForCausalLM
+    from long_vita_b200.synthetic import build_prompt
+
+    cfg, hf, _ = tiny
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "decode.pt")
+    mp.spawn(_cp_decode_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    ids, idx = build_prompt(cfg, 1, n_text=20, pad_multiple=2 * 2 * 128)
+    images = torch.randn(1, 3, 448, 448, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+    new = torch.randint(0, cfg.vocab_size, (3,), generator=torch.Generator().manual_seed(4))
+    with oracle_ops():
+        full = LongVITAForCausalLM(cfg, hf)(input_ids=torch.cat([ids, new.view(1, 3)], dim=1), images=images,
+                                           image_indices=idx).logits
+    S = ids.shape[1]
+    assert rel_fro(got["first"][0, 0], full[0, S - 1]) < 1e-2
+    for i in range(3):     # decode step i consumed new[i] at position S + i
+        assert rel_fro(got["steps"][0, i], full[0, S + i]) < 1.5e-2, (i, rel_fro(got["steps"][0, i], full[0, S + i]))
+        assert int(got["steps"][0, i].float().argmax()) == int(full[0, S + i].float().argmax())
