@@ -120,3 +120,42 @@ def test_context_parallel_backward_matches_single_device(lib_built, world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     mp.spawn(_bwd_worker, args=(world, _free_port()), nprocs=world, join=True)
+
+
+def _decode_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from long_vita_b200 import cp as CP
+        from long_vita_b200.config import LongVITAConfig
+        from long_vita_b200.hf.modeling import LongVITAForCausalLM
+        from long_vita_b200.synthetic import build_prompt, synthetic_frames
+        from long_vita_b200.weights import synthetic_state_dict
+
+        cfg = LongVITAConfig.tiny(layers=3, vit_layers=1)
+        w = synthetic_state_dict(cfg, seed=11, dtype=torch.bfloat16, perturb=True)
+        model = LongVITAForCausalLM(cfg, {k_: t.to(dev) for k_, t in w.items()})
+        ids, idx = build_prompt(cfg, 3, n_text=30, pad_multiple=2 * world * 128, seed=3)
+        images = synthetic_frames(cfg, 3, seed=3)
+        S = ids.shape[1]
+        new = torch.randint(0, cfg.vocab_size, (4,), generator=torch.Generator().manual_seed(6))
+        full = model(input_ids=torch.cat([ids, new.view(1, 4)], dim=1).to(dev), images=images.to(dev),
+                     image_indices=idx.to(dev)).logits
+        runner = CP.ContextParallelRunner(model, dist.group.WORLD)
+        first = runner.forward(ids.to(dev), images.to(dev), idx.to(dev), use_cache=True, max_new_tokens=16)
+        assert _rel(first[0, 0], full[0, S - 1]) < 1.5e-2
+        for i in range(4):
+            lg = runner.decode(new[i].to(dev))
+            assert _rel(lg[0, 0], full[0, S + i]) < 2e-2, (rank, i, _rel(lg[0, 0], full[0, S + i]))
+            assert int(lg[0, 0].float().argmax()) == int(full[0, S + i].float().argmax())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_context_parallel_sharded_cache_decode(lib_built, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    mp.spawn(_decode_worker, args=(world, _free_port()), nprocs=world, join=True)
