@@ -223,6 +223,15 @@ int lv_row_gather(const void* x, const int64_t* idx, void* out, int64_t n_idx, i
 int lv_row_scatter_zero(const void* x, const int64_t* idx, void* out, int64_t n_idx, int64_t n_rows_out,
                         int64_t cols, lv_stream_t stream);
 
+/* Merge of split-key partial attention results (flash-decoding, one new token against a K/V cache; the
+ * reference has no such path - it re-prefills every generated token, generation.py:127-135).
+ * o_part bf16 [n, G, hkv, d] and lse_part float [n, hkv, G] are what lv_attn_fwd returns when the G = hq/hkv
+ * query heads of a kv group are laid out as G query rows and the key range as n batch entries;
+ * out[h = kvh*G + g, :] = sum_s w_s o_part[s, g, kvh, :], w_s = exp(lse_s - LSE), LSE = logsumexp_s lse_s;
+ * lse_out float [hq] (may be NULL) receives LSE. */
+int lv_attn_decode_merge(const void* o_part, const float* lse_part, void* out, float* lse_out, int64_t n_splits,
+                         int64_t group, int64_t hkv, int64_t d, lv_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Dense linears (tensor-core roofline).  C[M,N] = act(A[M,K] . W[N,K]^T + bias[N]), bf16 in,
  * fp32 accumulate, bf16 out.  Replaces torch.matmul / te.Linear at layers.py:270,409, the ViT

@@ -380,6 +380,28 @@ __global__ void __launch_bounds__(128) row_copy_kernel(const __nv_bfloat16* __re
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Flash-decoding merge: one block per query head, one thread per head-dim column; every thread walks the
+// n_splits log-sum-exp values itself (n is ~18..150: cheaper than a block reduction).
+__global__ void __launch_bounds__(128) decode_merge_kernel(const __nv_bfloat16* __restrict__ o_part,
+                                                           const float* __restrict__ lse_part,
+                                                           __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out,
+                                                           int n, int G, int hkv, int d) {
+  const int kvh = blockIdx.x / G, g = blockIdx.x % G;
+  const int c = threadIdx.x;
+  float m = -INFINITY;
+  for (int s = 0; s < n; ++s) m = fmaxf(m, lse_part[((long long)s * hkv + kvh) * G + g]);
+  float sum = 0.f, acc = 0.f;
+  if (m > -INFINITY) {
+    for (int s = 0; s < n; ++s) {
+      const float w = __expf(lse_part[((long long)s * hkv + kvh) * G + g] - m);
+      sum += w;
+      if (c < d) acc = fmaf(w, __bfloat162float(o_part[(((long long)s * G + g) * hkv + kvh) * d + c]), acc);
+    }
+  }
+  if (c < d) out[((long long)kvh * G + g) * d + c] = __float2bfloat16_rn(sum > 0.f ? acc / sum : 0.f);
+  if (c == 0 && lse_out != nullptr) lse_out[kvh * G + g] = sum > 0.f ? m + __logf(sum) : -INFINITY;
+}
+
 }  // namespace lv
 
 using namespace lv;
@@ -570,6 +592,18 @@ int lv_row_scatter_zero(const void* x, const int64_t* idx, void* out, int64_t n_
   if (n_idx == 0) return LV_OK;
   row_copy_kernel<<<(unsigned)n_idx, 128, 0, s>>>(BF(x), nullptr, idx, BFM(out), n_idx, cols, n_idx, n_rows_out);
   LV_CHECK_LAUNCH("row_copy_kernel(scatter_zero)");
+  return LV_OK;
+}
+
+int lv_attn_decode_merge(const void* o_part, const float* lse_part, void* out, float* lse_out, int64_t n_splits,
+                         int64_t group, int64_t hkv, int64_t d, lv_stream_t stream) {
+  LV_CHECK_ARG(o_part && lse_part && out, "lv_attn_decode_merge: null pointer");
+  LV_CHECK_ARG(n_splits > 0 && group > 0 && hkv > 0 && d > 0 && d <= 128, "lv_attn_decode_merge: bad shape");
+  LV_CHECK_ARG(n_splits < (1ll << 20) && group * hkv < (1ll << 20), "lv_attn_decode_merge: too large");
+  LV_BIND_DEVICE(o_part);
+  decode_merge_kernel<<<(unsigned)(group * hkv), 128, 0, (cudaStream_t)stream>>>(BF(o_part), lse_part, BFM(out), lse_out,
+                                                                            (int)n_splits, (int)group, (int)hkv, (int)d);
+  LV_CHECK_LAUNCH("decode_merge_kernel");
   return LV_OK;
 }
 

@@ -256,14 +256,21 @@ def attention_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
         lses.append(l)
     o = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)              # [n, G, hkv, d]
     l = lses[0] if len(lses) == 1 else torch.cat(lses, dim=0)              # [n, hkv, G]
-    lse = torch.logsumexp(l, dim=0)                                        # [hkv, G]
-    if o.shape[0] == 1:
-        out = o[0]
-    else:
-        wgt = torch.exp(l - lse.unsqueeze(0)).permute(0, 2, 1).unsqueeze(-1)   # [n, G, hkv, 1]
-        out = (o.float() * wgt).sum(dim=0).to(torch.bfloat16)
-    out = out.transpose(0, 1).reshape(hq, d)                               # head h = kvh * G + g
-    return (out, lse.reshape(hq)) if return_lse else out
+    return decode_merge(o, l, return_lse=return_lse)
+
+
+def decode_merge(o_part: torch.Tensor, lse_part: torch.Tensor, return_lse: bool = False):
+    """o_part [n, G, hkv, d] bf16, lse_part [n, hkv, G] fp32 -> out [hq, d] (head h = kvh * G + g) and the
+    merged log-sum-exp [hq]: out = sum_s exp(lse_s - LSE) o_s (lv_attn_decode_merge)."""
+    _need_cuda_bf16(o_part)
+    _need_cuda(lse_part, torch.float32)
+    n, G, hkv, d = o_part.shape
+    o_part, lse_part = o_part.contiguous(), lse_part.contiguous()
+    out = torch.empty((hkv * G, d), dtype=torch.bfloat16, device=o_part.device)
+    lse = torch.empty((hkv * G,), dtype=torch.float32, device=o_part.device) if return_lse else None
+    _lib.check(_lib.lib().lv_attn_decode_merge(o_part.data_ptr(), lse_part.data_ptr(), out.data_ptr(), _ptr(lse), n, G, hkv, d,
+                                               _stream()), "lv_attn_decode_merge")
+    return (out, lse) if return_lse else out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -56,6 +56,14 @@ def _attention_bwd(d_out, q, k, v, out, lse, *, causal, scale=None, q_seg_len=No
     return _bf(dq), _bf(dk), _bf(dv)
 
 
+def _decode_merge(o_part, lse_part, return_lse=False):
+    n, G, hkv, d = o_part.shape
+    lse = torch.logsumexp(lse_part, dim=0)                                            # [hkv, G]
+    w = torch.exp(lse_part - lse.unsqueeze(0)).permute(0, 2, 1).unsqueeze(-1)          # [n, G, hkv, 1]
+    out = _bf((o_part.float() * w).sum(dim=0)).transpose(0, 1).reshape(hkv * G, d)
+    return (out, lse.reshape(hkv * G)) if return_lse else out
+
+
 def _rmsnorm(x, weight, eps=1e-6, residual=None):
     if residual is None:
         return O.rmsnorm(x, weight, eps)
@@ -117,6 +125,7 @@ def _row_scatter_zero(x, idx, n_rows_out):
 SUBSTITUTES = {
     "attention_fwd": _attention_fwd,
     "attention_bwd": _attention_bwd,
+    "decode_merge": _decode_merge,
     "rmsnorm": _rmsnorm,
     "layernorm": lambda x, w, b, eps=1e-6: O.layernorm(x, w, b, eps),
     "rope_table": _rope_table,
