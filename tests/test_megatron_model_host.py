@@ -154,8 +154,6 @@ def test_guards(tiny, model):
     with oracle_ops():
         with pytest.raises(AssertionError):
             model(ids, pos, None, packed_seq_params=object())
-        with pytest.raises(NotImplementedError):
-            model(ids, pos, None, inference_params=types.SimpleNamespace(key_value_memory_dict={1: 2}))
         with pytest.raises(AssertionError):
             model.embedding(ids, pos, {"features": torch.zeros(1, 256, cfg.hidden_size), "bogus": 1})
 
@@ -553,3 +551,27 @@ def test_two_rank_sharded_cache_decode_equals_full_forward(tiny, tmp_path):
     for i in range(3):     # decode step i consumed new[i] at position S + i
         assert rel_fro(got["steps"][0, i], full[0, S + i]) < 1.5e-2, (i, rel_fro(got["steps"][0, i], full[0, S + i]))
         assert int(got["steps"][0, i].float().argmax()) == int(full[0, S + i].float().argmax())
+
+
+def test_megatron_kv_cache_protocol_matches_full_forward(tiny, model):
+    """Megatron's `--use-kv-cache` loop (generation.py:127-131): the first call carries the prompt and the external
+    inputs, later calls only the new tokens and their positions, all sharing one `inference_params`.  The logits
+    of every step must equal the full forward over the extended sequence."""
+    cfg, hf, _ = tiny
+    ids, images, idx = _inputs(cfg)
+    s = ids.shape[1]
+    new = torch.randint(0, cfg.vocab_size, (1, 3), generator=torch.Generator().manual_seed(12))
+    ext = {"images": images, "indices": idx}
+    ip = types.SimpleNamespace(external_inputs=ext, key_value_memory_dict={}, logit_mask=None, use_kv_cache=True,
+                               max_sequence_length=s + 8)
+    with oracle_ops():
+        full = model(torch.cat([ids, new], dim=1), torch.arange(s + 3).unsqueeze(0), None, external_inputs=ext)
+        first = model(ids, torch.arange(s).unsqueeze(0), None, inference_params=ip)
+        cache = ip.key_value_memory_dict["b200_kv_cache"]
+        assert len(cache) == s and cache.capacity == s + 8
+        assert rel_fro(first[0], full[0, :s]) < 1e-6 or torch.equal(first[0], full[0, :s])
+        for i in range(3):
+            step = model(new[:, i : i + 1], torch.tensor([[s + i]]), None, inference_params=ip)   # external inputs ignored now
+            assert step.shape == (1, 1, cfg.vocab_size) and len(cache) == s + i + 1
+            assert rel_fro(step[0, 0], full[0, s + i]) < 1e-2, i
+            assert int(step[0, 0].float().argmax()) == int(full[0, s + i].float().argmax())
