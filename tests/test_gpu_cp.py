@@ -60,6 +60,26 @@ def _worker(rank, world, port):
             assert math.sqrt(max(e * e - e_floor * e_floor, 0.0)) < 2e-3, (rank, epoch, e, e_floor)
         dist.barrier()
 
+        # ---- the 14B K/V geometry (8 kv heads x 128 = 4 KB K|V rows): the copier's one-row-per-pass fast path ----
+        hq2, hkv2 = 40, 8
+        S2 = 2 * world * 128
+        ctx2 = CP.CPContext(dist.group.WORLD, S2, hq2, hkv2, d, dev)
+        own2 = CP.zigzag_index(S2, world, rank)
+        for epoch in range(2):
+            g = torch.Generator().manual_seed(300 + epoch)
+            qkv = torch.randn(S2, (hq2 + 2 * hkv2) * d, generator=g).to(torch.bfloat16)
+            ctx2.qkv_buffer().copy_(qkv[own2].to(dev))
+            out = ctx2.attention()
+            q = qkv[:, : hq2 * d].view(1, S2, hq2, d)
+            k = qkv[:, hq2 * d : (hq2 + hkv2) * d].view(1, S2, hkv2, d)
+            v = qkv[:, (hq2 + hkv2) * d :].view(1, S2, hkv2, d)
+            ref, _ = O.attention(q, k, v, causal=True)
+            ref_l = ref[0, own2].reshape(own2.numel(), hq2 * d)
+            e = _rel(out, ref_l)
+            e_floor = _rel(ref_l.to(torch.bfloat16), ref_l)
+            assert math.sqrt(max(e * e - e_floor * e_floor, 0.0)) < 2e-3, (rank, epoch, e, e_floor)
+        dist.barrier()
+
         # ---- whole sharded prefill vs the single-device forward ----
         cfg = LongVITAConfig.tiny(layers=3, vit_layers=1)
         w = synthetic_state_dict(cfg, seed=11, dtype=torch.bfloat16, perturb=True)
