@@ -173,3 +173,33 @@ def test_generate_greedy_matches_re_prefill(setup):
             want.append(int(tok))
             seq = torch.cat([seq, tok.view(1, 1)], dim=1)
     assert gen.shape == (1, 3) and gen[0].tolist() == want
+
+
+def test_kv_cache_decode_against_the_references_own_incremental_decoding():
+    """The build's decode path (prefill with use_cache, then single-token steps through ops.attention_decode; kernels
+    replaced by the oracle) against the committed logits of the reference's own DynamicCache decoding
+    (tests/golden/ref_long_vita_decode.pt)."""
+    import os
+    import sys
+
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold_dir)
+    from make_golden import decode_new_tokens, long_vita_inputs
+
+    dec = torch.load(os.path.join(gold_dir, "ref_long_vita_decode.pt"))
+    cfg = LongVITAConfig.tiny(layers=2, vit_layers=1)
+    w = synthetic_state_dict(cfg, seed=dec["seed"], dtype=torch.float32, perturb=True)
+    ids, images, idx = long_vita_inputs(cfg, dec["seed"])
+    new = decode_new_tokens(cfg)
+    model = LongVITAForCausalLM(cfg, {k: v.to(torch.bfloat16) for k, v in w.items()})
+    with oracle_ops():
+        out = model(input_ids=ids, images=images.to(torch.bfloat16), image_indices=idx, use_cache=True, num_logits_to_keep=1,
+                    max_cache_len=ids.shape[1] + 8)
+        assert rel_fro(out.logits[0, -1], dec["prefill_last"]) < 2e-2
+        cache = out.past_key_values
+        for i in range(new.shape[1]):
+            o = model(input_ids=new[:, i : i + 1], past_key_values=cache, use_cache=True, images=images.to(torch.bfloat16),
+                      image_indices=idx)
+            assert rel_fro(o.logits[0, 0], dec["steps"][i]) < 2e-2, (i, rel_fro(o.logits[0, 0], dec["steps"][i]))
+            assert int(o.logits[0, 0].float().argmax()) == int(dec["steps"][i].argmax())
+        assert len(cache) == dec["cache_len"]
