@@ -1221,7 +1221,6 @@ extern "C" int lv_attn_fwd(const lv_attn_params* a, lv_stream_t stream) {
 extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv_stream_t stream) {
   int rc = check_attn_params(a);
   if (rc) return rc;
-  LV_BIND_DEVICE(a->q);
   LV_CHECK_ARG(c != nullptr, "lv_attn_cp_fwd: null cp params");
   LV_CHECK_ARG(c->cp >= 2 && c->cp <= 8 && c->rank >= 0 && c->rank < c->cp, "lv_attn_cp_fwd: bad rank %d / cp %d", c->rank, c->cp);
   LV_CHECK_ARG(a->batch == 1 && a->causal, "lv_attn_cp_fwd: batch 1, causal only");
@@ -1251,6 +1250,7 @@ extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv
     k.peer_kv[p] = reinterpret_cast<const __nv_bfloat16*>(c->peer_kv[p]);
     k.peer_ready[p] = reinterpret_cast<uint32_t*>(c->peer_ready[p]) + parity * 8 + c->rank;
   }
+  LV_BIND_DEVICE(a->q);     // after every argument check, so that bad arguments are reported without touching CUDA
   k.my_ready = reinterpret_cast<const uint32_t*>(c->my_ready) + parity * 8;
   k.k_full = reinterpret_cast<__nv_bfloat16*>(c->k_full);
   k.v_full = reinterpret_cast<__nv_bfloat16*>(c->v_full);

@@ -108,3 +108,21 @@ def test_backward_and_gemm_argument_errors(lib_built):
     assert h.lv_attn_bwd(ctypes.byref(b), None) == -1 and b"required" in h.lv_last_error()
     assert h.lv_gemm_bias_act(1, 1, None, 1, 4, 24, 8, 8, 8, 24, 3, None) == -1 and b"SwiGLU" in h.lv_last_error()
     assert h.lv_gemm_bias_act(1, 1, None, 1, 4, 16, 8, 8, 8, 16, 7, None) == -1 and b"unknown activation" in h.lv_last_error()
+
+
+def test_context_parallel_argument_errors(lib_built):
+    from long_vita_b200 import _lib
+    from long_vita_b200._lib import CpParams
+
+    h = _lib.lib()
+    a = _attn_params()
+    c = CpParams()
+    c.rank, c.cp, c.seq_total = 0, 9, 4096
+    assert h.lv_attn_cp_fwd(ctypes.byref(a), ctypes.byref(c), None) == -1 and b"bad rank" in h.lv_last_error()
+    c.cp = 2
+    c.seq_total = 4098
+    assert h.lv_attn_cp_fwd(ctypes.byref(a), ctypes.byref(c), None) == -1 and b"not divisible by 2*cp" in h.lv_last_error()
+    c.seq_total = 4 * 100
+    assert h.lv_attn_cp_fwd(ctypes.byref(a), ctypes.byref(c), None) == -1 and b"multiple of 128" in h.lv_last_error()
+    c.seq_total = 4 * 128
+    assert h.lv_attn_cp_fwd(ctypes.byref(a), ctypes.byref(c), None) == -1 and b"staging buffers" in h.lv_last_error()
