@@ -45,6 +45,7 @@ struct AttnKParams {
   int n_qblk;      // ceil(sq / 256)
   int n_items;     // batch * hq * n_qblk
   int block_major; // 1: order work items (q-block, kv-head, head) - global longest-first; 0: (kv-head, q-block, head)
+  int serpentine;  // 1: odd rounds sweep the item list backwards (default); LV_ATTN_SCHED=0 turns it off for A/B runs
   int poly_exp;    // 1: every 4th exponential of the softmax runs on the FMA pipe (polynomial), the rest on MUFU
   float* lse;
 };
@@ -255,10 +256,10 @@ struct AttnCfg {
 // Static work assignment: the item list is sorted longest-first; CTAs sweep it boustrophedon (round r
 // forwards, round r+1 backwards) so every CTA receives a near-equal share of causal work without a
 // global atomic.  All warp roles of a CTA evaluate the same sequence.
-__device__ __forceinline__ int sched_item(int round, int n_items) {
+__device__ __forceinline__ int sched_item(int round, int n_items, int serpentine) {
   const int base = round * (int)gridDim.x;
   if (base >= n_items) return -1;
-  const int item = base + ((round & 1) ? ((int)gridDim.x - 1 - (int)blockIdx.x) : (int)blockIdx.x);
+  const int item = base + ((serpentine && (round & 1)) ? ((int)gridDim.x - 1 - (int)blockIdx.x) : (int)blockIdx.x);
   return item < n_items ? item : -1;
 }
 
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     if (lane == 0) {
       uint32_t item_cnt = 0, kcnt = 0, vcnt = 0;
       int ready_upto = 0;   // CP: key blocks [0, ready_upto) are known to be staged
-      for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
+      for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
         const WorkItem w = decode_item(p, item);
         const int nmax = max(w.n[0], w.n[1]);
         for (int t = 0; t < 2; ++t) {
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         __syncwarp();
       };
 
-      for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
+      for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
         const WorkItem w = decode_item(p, item);
         const int n0 = w.n[0], n1 = w.n[1];
         const int nmax = max(n0, n1);
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     uint8_t* stage = sQ + t * Cfg::TILE_BYTES;
     uint32_t item_cnt = 0, scnt = 0, ocnt = 0;
 
-    for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
+    for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
       const WorkItem w = decode_item(p, item);
       const int n = w.n[t];
       const long long qpos = w.qpos[t] + row;           // global position of this thread's query row
@@ -816,7 +817,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     if (lane == 0) {
       uint32_t item_cnt = 0, kcnt = 0, vcnt = 0;
       int ready_upto = 0;
-      for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
+      for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
         const WorkItem2 w = decode_item2(p, item);
         const int ntile = (max(w.n[0], w.n[1]) + 1) / 2;   // 128-row K/V tiles
         for (int t = 0; t < 2; ++t) {
@@ -862,7 +863,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
       uint32_t item_cnt = 0;
       uint32_t kbase = 0, vbase = 0;            // ring counters of this item's tile 0
       uint32_t scnt[2][2] = {{0, 0}, {0, 0}};   // completed uses of s_full / p_full [tile][buffer]
-      for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
+      for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
         const WorkItem2 w = decode_item2(p, item);
         const int nmax = max(w.n[0], w.n[1]);
         const int ntile = (nmax + 1) / 2;
@@ -953,7 +954,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     uint32_t scnt[2] = {0, 0};   // uses of s_full[t][b]
     uint32_t pv_base = 0;        // PV commits on o_done[t] before this item
 
-    for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
+    for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
       const WorkItem2 w = decode_item2(p, item);
       const int n = w.n[t];
       const long long qpos = w.qpos[t] + row;
@@ -1143,6 +1144,11 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
   p.block_major = (a->causal && a->sk * a->hkv * a->d * 4 <= (64ll << 20)) ? 1 : 0;
   p.lse = a->lse;
   p.poly_exp = attn_poly_exp();
+  static const int serp = [] {
+    const char* e = getenv("LV_ATTN_SCHED");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  p.serpentine = serp;
   static bool attr_set = false;
   if (!attr_set) {
     if constexpr (VER == 2) {

@@ -36,6 +36,9 @@ $T 200 python tools/bench_bwd.py > gpurun_out/r2_bwd.log 2>&1
 echo "== bwd exit $?"; tail -n 6 gpurun_out/r2_bwd.log
 LV_GEMM_GM=32 $T 200 python tools/bench_kernels.py --only gemm --quick --out gpurun_out/r2_gemm_gm32.json > gpurun_out/r2_gemm_gm32.log 2>&1
 echo "== gemm with 32-M-block rasterisation groups (LV_GEMM_GM=32) exit $?"; cut -c1-170 gpurun_out/r2_gemm_gm32.log | tail -n 8
+# 3c. work-item order A/B at the model's own shape: serpentine (default) vs plain round-robin, in the bench step
+LV_ATTN_SCHED=0 $T 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_n1_sched0.json 2> gpurun_out/r2_bench_n1_sched0.err
+echo "== bench with LV_ATTN_SCHED=0 exit $?"; cut -c1-300 gpurun_out/r2_bench_n1_sched0.json
 # 4. the headline
 $T 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
 echo "== bench exit $?"; cut -c1-600 gpurun_out/r2_bench_n1.json
