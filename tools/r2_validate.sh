@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of round 2: validate the r2-prep kernel changes (warp-uniform MMA issue) on ONE GPU.
-#   gpurun --timeout 1500 -- 'bash tools/r2_validate.sh'
+#   gpurun --timeout 1800 -- 'bash tools/r2_validate.sh'
 # Every step runs under its own timeout; a hang in a new kernel costs at most that step.
 mkdir -p gpurun_out
 T="timeout -k 5"
