@@ -174,7 +174,11 @@ __device__ __forceinline__ void cp_copier(const CpKParams& cpp, int warp, int la
         const int lrow0 = (chunk < cpp.cp ? 0 : cpp.chunk) + (tok0 - chunk * cpp.chunk);
         if (!(seen & (1u << owner))) {
           if (lane == 0)
-            while (ld_acquire_sys(cpp.my_ready + owner) < cpp.epoch1) {
+            {
+              [[maybe_unused]] uint32_t spins = 0;
+              while (ld_acquire_sys(cpp.my_ready + owner) < cpp.epoch1) {
+                LV_SPIN_GUARD(spins, "peer ready word", cpp.my_ready + owner, cpp.epoch1)
+              }
             }
           __syncwarp();
           seen |= 1u << owner;
@@ -234,8 +238,12 @@ __device__ __forceinline__ void cp_copier(const CpKParams& cpp, int warp, int la
         // do not retire before every peer has entered this epoch: a peer's flag for epoch e+1 then
         // proves it finished reading our epoch e-1 rows (buffer parity reuse)
         if (lane < cpp.cp && lane != cpp.rank)
+        {
+          [[maybe_unused]] uint32_t spins = 0;
           while (ld_acquire_sys(cpp.my_ready + lane) < cpp.epoch1) {
+            LV_SPIN_GUARD(spins, "peer epoch word (exit)", cpp.my_ready + lane, cpp.epoch1)
           }
+        }
         __syncwarp();
       }
 }
@@ -399,7 +407,11 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         }
         for (int j = 0; j < nmax; ++j) {
           if (CP && j >= ready_upto) {
-            while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1 * CP_SUB) {
+            {
+              [[maybe_unused]] uint32_t spins = 0;
+              while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1 * CP_SUB) {
+                LV_SPIN_GUARD(spins, "staged block flag", cpp.blk_flags + j, cpp.epoch1 * CP_SUB)
+              }
             }
             ready_upto = j + 1;
             fence_proxy_async_all();   // copier warps wrote the staging rows through the generic proxy
@@ -829,7 +841,11 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         }
         for (int j = 0; j < ntile; ++j) {
           if (CP && j >= ready_upto) {
-            while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1 * CP_SUB) {
+            {
+              [[maybe_unused]] uint32_t spins = 0;
+              while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1 * CP_SUB) {
+                LV_SPIN_GUARD(spins, "staged block flag", cpp.blk_flags + j, cpp.epoch1 * CP_SUB)
+              }
             }
             ready_upto = j + 1;
             fence_proxy_async_all();

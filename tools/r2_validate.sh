@@ -4,7 +4,10 @@
 # Every step runs under its own timeout; a hang in a new kernel costs at most that step.
 mkdir -p gpurun_out
 T="timeout -k 5"
-$T 120 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { tail -20 gpurun_out/build.log; exit 1; }
+# Parity runs on the WATCHDOG build (csrc/ptx.cuh: a wait that spins ~1 s prints which barrier of which warp is
+# stuck and traps - a protocol bug costs one error line, not a hung GPU); ship it prebuilt
+# (`LV_WATCHDOG=1 python long-vita_b200/build.py` before gpurun) or let this line build it (~40 s of box time).
+LV_WATCHDOG=1 $T 300 python long-vita_b200/build.py > gpurun_out/build_watchdog.log 2>&1 || { tail -20 gpurun_out/build_watchdog.log; exit 1; }
 # 1. smallest possible smoke of each touched kernel first (fast fail)
 $T 90 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "== smoke exit $?"; tail -n 3 gpurun_out/smoke.log
@@ -16,6 +19,8 @@ echo "== all 1-GPU tests exit $?"; tail -n 6 gpurun_out/test_all.log
 # 2b. the double-buffered-S kernel (v2) shares the new issue path: parity before it is timed
 LV_ATTN_VERSION=2 $T 200 python -m pytest tests/test_gpu_attention.py -m gpu -q -x --timeout 90 --timeout-method=thread > gpurun_out/test_attn_v2.log 2>&1
 echo "== attention parity v2: exit $?"; tail -n 4 gpurun_out/test_attn_v2.log
+# ---- timing runs use the release build (no printf / trap code in the wait loops) ----
+LV_WATCHDOG=0 $T 300 python long-vita_b200/build.py > gpurun_out/build_release.log 2>&1 || { tail -20 gpurun_out/build_release.log; exit 1; }
 # 3. speed: attention v1 / v2 / v3, GEMM, backward
 for V in 1 2 3; do
   LV_ATTN_VERSION=$V $T 200 python tools/bench_kernels.py --only attn --quick --out gpurun_out/r2_attn_v$V.json > gpurun_out/r2_attn_v$V.log 2>&1
