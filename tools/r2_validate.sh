@@ -19,6 +19,9 @@ echo "== all 1-GPU tests exit $?"; tail -n 6 gpurun_out/test_all.log
 # 2b. the double-buffered-S kernel (v2) shares the new issue path: parity before it is timed
 LV_ATTN_VERSION=2 $T 200 python -m pytest tests/test_gpu_attention.py -m gpu -q -x --timeout 90 --timeout-method=thread > gpurun_out/test_attn_v2.log 2>&1
 echo "== attention parity v2: exit $?"; tail -n 4 gpurun_out/test_attn_v2.log
+# 2c. the pipelined backward kernel (LV_BWD_VERSION=2): parity on the watchdog build
+LV_BWD_VERSION=2 $T 240 python -m pytest tests/test_gpu_attention_bwd.py -m gpu -q -x --timeout 90 --timeout-method=thread > gpurun_out/test_bwd_v2.log 2>&1
+echo "== backward v2 parity: exit $?"; tail -n 6 gpurun_out/test_bwd_v2.log
 # ---- timing runs use the release build (no printf / trap code in the wait loops) ----
 LV_WATCHDOG=0 $T 300 python long-vita_b200/build.py > gpurun_out/build_release.log 2>&1 || { tail -20 gpurun_out/build_release.log; exit 1; }
 # 3. speed: attention v1 / v2 / v3, GEMM, backward
@@ -39,6 +42,8 @@ LV_GEMV=0 $T 200 python tools/bench_kernels.py --only gemm --quick --out gpurun_
 echo "== gemm (LM head through the tensor-core kernel, LV_GEMV=0) exit $?"; grep -i "lm\|152064" gpurun_out/r2_gemm_nogemv.log | cut -c1-170 | tail -n 3
 $T 200 python tools/bench_bwd.py > gpurun_out/r2_bwd.log 2>&1
 echo "== bwd exit $?"; tail -n 6 gpurun_out/r2_bwd.log
+LV_BWD_VERSION=2 $T 200 python tools/bench_bwd.py > gpurun_out/r2_bwd_v2.log 2>&1
+echo "== bwd v2 exit $?"; tail -n 6 gpurun_out/r2_bwd_v2.log
 LV_GEMM_GM=32 $T 200 python tools/bench_kernels.py --only gemm --quick --out gpurun_out/r2_gemm_gm32.json > gpurun_out/r2_gemm_gm32.log 2>&1
 echo "== gemm with 32-M-block rasterisation groups (LV_GEMM_GM=32) exit $?"; cut -c1-170 gpurun_out/r2_gemm_gm32.log | tail -n 8
 # 3c. work-item order A/B at the model's own shape: serpentine (default) vs plain round-robin, in the bench step
