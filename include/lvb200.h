@@ -223,6 +223,16 @@ int lv_row_gather(const void* x, const int64_t* idx, void* out, int64_t n_idx, i
 int lv_row_scatter_zero(const void* x, const int64_t* idx, void* out, int64_t n_idx, int64_t n_rows_out,
                         int64_t cols, lv_stream_t stream);
 
+/* Backward of the token-wise operators (training through the `--spec` layer).
+ * RMSNorm: g = dy*w, dx = rstd*(g - xhat*mean(g*xhat)) (+ add_in, the gradient arriving on the residual stream),
+ * dw partial sums in `dw_partials` [lv_rmsnorm_bwd_partials(rows, cols), cols] float - the caller adds the rows
+ * (no atomics: bit-reproducible).  x is the tensor that was normalised (after the fused residual add).
+ * SwiGLU: gate_up = cat(gate, up) as in lv_swiglu; d_gate_up in the same layout. */
+int64_t lv_rmsnorm_bwd_partials(int64_t rows, int64_t cols);
+int lv_rmsnorm_bwd(const void* x, const void* w, const void* dy, const void* add_in, void* dx, float* dw_partials,
+                   int64_t rows, int64_t cols, float eps, lv_stream_t stream);
+int lv_swiglu_bwd(const void* gate_up, const void* dh, void* d_gate_up, int64_t rows, int64_t inter, lv_stream_t stream);
+
 /* Merge of split-key partial attention results (flash-decoding, one new token against a K/V cache; the
  * reference has no such path - it re-prefills every generated token, generation.py:127-135).
  * o_part bf16 [n, G, hkv, d] and lse_part float [n, hkv, G] are what lv_attn_fwd returns when the G = hq/hkv

@@ -564,6 +564,131 @@ def masked_linear_autograd(h: torch.Tensor, weight: torch.Tensor, logit_mask: to
     return _MaskedLinearFn.apply(h, weight, logit_mask)
 
 
+# ------------------------------------------------------------------------------------------------
+# differentiable building blocks of the decoder layer (training through the `--spec` layer)
+# ------------------------------------------------------------------------------------------------
+def rmsnorm_bwd(x: torch.Tensor, weight: torch.Tensor, dy: torch.Tensor, eps: float = 1e-6,
+                add_in: Optional[torch.Tensor] = None):
+    """Gradients of rmsnorm(x, weight): returns (dx [+ add_in], dweight).  `x` is the tensor that was normalised."""
+    _need_cuda_bf16(x, weight, dy, add_in)
+    cols = x.shape[-1]
+    x2, dy2 = x.reshape(-1, cols).contiguous(), dy.reshape(-1, cols).contiguous()
+    a2 = None if add_in is None else add_in.reshape(-1, cols).contiguous()
+    rows = x2.shape[0]
+    parts = int(_lib.lib().lv_rmsnorm_bwd_partials(rows, cols))
+    dw_part = torch.empty((parts, cols), dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x2)
+    _lib.check(_lib.lib().lv_rmsnorm_bwd(x2.data_ptr(), weight.data_ptr(), dy2.data_ptr(), _ptr(a2), dx.data_ptr(),
+                                         dw_part.data_ptr(), rows, cols, float(eps), _stream()), "lv_rmsnorm_bwd")
+    return dx.view(x.shape), dw_part.sum(dim=0).to(torch.bfloat16)
+
+
+def swiglu_bwd(gate_up: torch.Tensor, dh: torch.Tensor):
+    _need_cuda_bf16(gate_up, dh)
+    inter = gate_up.shape[-1] // 2
+    g2, d2 = gate_up.reshape(-1, 2 * inter).contiguous(), dh.reshape(-1, inter).contiguous()
+    out = torch.empty_like(g2)
+    _lib.check(_lib.lib().lv_swiglu_bwd(g2.data_ptr(), d2.data_ptr(), out.data_ptr(), g2.shape[0], inter, _stream()),
+               "lv_swiglu_bwd")
+    return out.view(gate_up.shape)
+
+
+class _RMSNormFn(torch.autograd.Function):
+    """y = rmsnorm(x [+ residual]); with a residual also returns the sum (the new residual stream)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, eps):
+        if residual is None:
+            y, s = rmsnorm(x, weight, eps), x
+        else:
+            y, s = rmsnorm(x, weight, eps, residual=residual)
+        ctx.save_for_backward(s, weight)
+        ctx.eps, ctx.has_res = eps, residual is not None
+        return (y, s) if residual is not None else y
+
+    @staticmethod
+    def backward(ctx, dy, ds=None):
+        s, weight = ctx.saved_tensors
+        dx, dw = rmsnorm_bwd(s, weight, dy.contiguous(), ctx.eps, add_in=ds if ctx.has_res else None)
+        return dx, (dx if ctx.has_res else None), dw, None
+
+
+def rmsnorm_autograd(x, weight, eps: float = 1e-6, residual=None):
+    return _RMSNormFn.apply(x, residual, weight, eps)
+
+
+class _SwiGLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate_up):
+        ctx.save_for_backward(gate_up)
+        return swiglu(gate_up)
+
+    @staticmethod
+    def backward(ctx, dh):
+        (gate_up,) = ctx.saved_tensors
+        return swiglu_bwd(gate_up, dh.contiguous())
+
+
+def swiglu_autograd(gate_up):
+    return _SwiGLUFn.apply(gate_up)
+
+
+class _RopeFn(torch.autograd.Function):
+    """rotate-half RoPE is linear in x: the gradient is the same rotation with -sin."""
+
+    @staticmethod
+    def forward(ctx, x, cos, sin):
+        ctx.save_for_backward(cos, sin)
+        return rope(x, cos, sin)
+
+    @staticmethod
+    def backward(ctx, dy):
+        cos, sin = ctx.saved_tensors
+        dy = dy if dy.stride(2) == 1 else dy.contiguous()
+        return rope(dy, cos, -sin), None, None
+
+
+def rope_autograd(x, cos, sin):
+    return _RopeFn.apply(x, cos, sin)
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM; dX = dY W and dW = dY^T X reuse the same kernel on operands transposed once
+    per call (the [N, K] operand of each product must be K-contiguous); the token count is zero-padded to a multiple
+    of 8 for the weight gradient (the GEMM's K granularity)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        n_out, k_in = weight.shape
+        dy2 = dy.reshape(-1, n_out).contiguous()
+        x2 = x.reshape(-1, k_in)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = linear(dy2, weight.t().contiguous()).view(x.shape)          # [T, K] = dY [T, N] . (W^T)[K, N]^T
+        if ctx.needs_input_grad[1]:
+            t = dy2.shape[0]
+            tp = (t + 7) // 8 * 8
+            dyt = torch.zeros((n_out, tp), dtype=torch.bfloat16, device=dy.device)
+            dyt[:, :t] = dy2.t()
+            xt = torch.zeros((k_in, tp), dtype=torch.bfloat16, device=dy.device)
+            xt[:, :t] = x2.t()
+            dw = linear(dyt, xt)                                             # [N, K] = dY^T [N, T] . (X^T)[K, T]^T
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.float().sum(dim=0).to(torch.bfloat16)
+        return dx, dw, db
+
+
+def linear_autograd(x, weight, bias=None):
+    return _LinearFn.apply(x, weight, bias)
+
+
 def patch_embed(images: torch.Tensor, w_pad: torch.Tensor, bias: Optional[torch.Tensor], cls: torch.Tensor,
                 pos: torch.Tensor, patch: int):
     """images [n,3,S,S] -> [n, 1 + (S/patch)^2, C] (conv-as-GEMM + cls + position embedding).

@@ -64,6 +64,23 @@ def _decode_merge(o_part, lse_part, return_lse=False):
     return (out, lse.reshape(hkv * G)) if return_lse else out
 
 
+def _rmsnorm_bwd(x, weight, dy, eps=1e-6, add_in=None):
+    with torch.enable_grad():
+        xf = x.detach().float().requires_grad_(True)
+        wf = weight.detach().float().requires_grad_(True)
+        y = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps) * wf
+        y.backward(dy.float())
+    dx = xf.grad if add_in is None else xf.grad + add_in.float()
+    return _bf(dx), _bf(wf.grad)
+
+
+def _swiglu_bwd(gate_up, dh):
+    with torch.enable_grad():
+        gu = gate_up.detach().float().requires_grad_(True)
+        O.swiglu(gu).backward(dh.float())
+    return _bf(gu.grad)
+
+
 def _rmsnorm(x, weight, eps=1e-6, residual=None):
     if residual is None:
         return O.rmsnorm(x, weight, eps)
@@ -127,6 +144,8 @@ SUBSTITUTES = {
     "attention_bwd": _attention_bwd,
     "decode_merge": _decode_merge,
     "rmsnorm": _rmsnorm,
+    "rmsnorm_bwd": _rmsnorm_bwd,
+    "swiglu_bwd": _swiglu_bwd,
     "layernorm": lambda x, w, b, eps=1e-6: O.layernorm(x, w, b, eps),
     "rope_table": _rope_table,
     "rope": _rope,
