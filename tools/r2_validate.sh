@@ -14,8 +14,8 @@ echo "== smoke exit $?"; tail -n 3 gpurun_out/smoke.log
 # 2. parity suites of the touched kernels
 $T 300 python -m pytest tests/test_gpu_attention.py tests/test_gpu_gemm.py tests/test_gpu_attention_bwd.py -m gpu -q -x --timeout 90 --timeout-method=thread > gpurun_out/test_kernels.log 2>&1
 echo "== kernel parity exit $?"; tail -n 6 gpurun_out/test_kernels.log
-$T 400 python -m pytest tests -m gpu -q -x --timeout 120 --timeout-method=thread --deselect tests/test_gpu_cp.py > gpurun_out/test_all.log 2>&1
-echo "== all 1-GPU tests exit $?"; tail -n 6 gpurun_out/test_all.log
+$T 600 python -m pytest tests -m gpu -q --timeout 120 --timeout-method=thread --deselect tests/test_gpu_cp.py -rf > gpurun_out/test_all.log 2>&1   # no -x: see every failing feature in one call
+echo "== all 1-GPU tests exit $?"; tail -n 25 gpurun_out/test_all.log
 # 2b. the double-buffered-S kernel (v2) shares the new issue path: parity before it is timed
 LV_ATTN_VERSION=2 $T 200 python -m pytest tests/test_gpu_attention.py -m gpu -q -x --timeout 90 --timeout-method=thread > gpurun_out/test_attn_v2.log 2>&1
 echo "== attention parity v2: exit $?"; tail -n 4 gpurun_out/test_attn_v2.log
