@@ -139,7 +139,8 @@ typedef struct lv_cp_params {
   void* my_ready;            /* local base of the same array */
   void* k_full;              /* bf16 [S, hkv*d] staging (local) */
   void* v_full;
-  void* blk_flags;           /* uint32 [S/128], zero-initialised once */
+  void* blk_flags;           /* uint32 [S/128], zero-initialised once; private to the kernel (it counts
+                              * staged 32-token units: 4 * (epoch + 1) when block b of this epoch is whole) */
 } lv_cp_params;
 
 int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv_stream_t stream);
@@ -221,6 +222,25 @@ int lv_row_gather(const void* x, const int64_t* idx, void* out, int64_t n_idx, i
                   lv_stream_t stream);
 int lv_row_scatter_zero(const void* x, const int64_t* idx, void* out, int64_t n_idx, int64_t n_rows_out,
                         int64_t cols, lv_stream_t stream);
+
+/* Backward of the token-wise operators (training through the `--spec` layer).
+ * RMSNorm: g = dy*w, dx = rstd*(g - xhat*mean(g*xhat)) (+ add_in, the gradient arriving on the residual stream),
+ * dw partial sums in `dw_partials` [lv_rmsnorm_bwd_partials(rows, cols), cols] float - the caller adds the rows
+ * (no atomics: bit-reproducible).  x is the tensor that was normalised (after the fused residual add).
+ * SwiGLU: gate_up = cat(gate, up) as in lv_swiglu; d_gate_up in the same layout. */
+int64_t lv_rmsnorm_bwd_partials(int64_t rows, int64_t cols);
+int lv_rmsnorm_bwd(const void* x, const void* w, const void* dy, const void* add_in, void* dx, float* dw_partials,
+                   int64_t rows, int64_t cols, float eps, lv_stream_t stream);
+int lv_swiglu_bwd(const void* gate_up, const void* dh, void* d_gate_up, int64_t rows, int64_t inter, lv_stream_t stream);
+
+/* Merge of split-key partial attention results (flash-decoding, one new token against a K/V cache; the
+ * reference has no such path - it re-prefills every generated token, generation.py:127-135).
+ * o_part bf16 [n, G, hkv, d] and lse_part float [n, hkv, G] are what lv_attn_fwd returns when the G = hq/hkv
+ * query heads of a kv group are laid out as G query rows and the key range as n batch entries;
+ * out[h = kvh*G + g, :] = sum_s w_s o_part[s, g, kvh, :], w_s = exp(lse_s - LSE), LSE = logsumexp_s lse_s;
+ * lse_out float [hq] (may be NULL) receives LSE. */
+int lv_attn_decode_merge(const void* o_part, const float* lse_part, void* out, float* lse_out, int64_t n_splits,
+                         int64_t group, int64_t hkv, int64_t d, lv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense linears (tensor-core roofline).  C[M,N] = act(A[M,K] . W[N,K]^T + bias[N]), bf16 in,

@@ -28,6 +28,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("LV_WATCHDOG") == "1":      # debug build: stuck waits report themselves and trap (csrc/ptx.cuh)
+    NVCC_FLAGS.append("-DLV_WATCHDOG")
+
+
 def _nvcc() -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
@@ -40,12 +44,13 @@ def _sources():
 
 
 def _digest(paths) -> str:
+    """Content hash of the sources (file names, not absolute paths: gpurun runs the snapshot from another
+    directory, and the library built here must be accepted there instead of being rebuilt on GPU time)."""
     h = hashlib.sha256()
-    for p in sorted(paths):
+    for p in sorted(paths, key=os.path.basename):
         with open(p, "rb") as f:
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -57,8 +62,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers.append(os.path.join(HERE, "..", "include", "lvb200.h"))
     stamp = os.path.join(OBJDIR, "stamp")
     digest = _digest(srcs + headers)
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
-        return LIB
+    flags = " ".join(NVCC_FLAGS)
+    if not force and os.path.exists(LIB) and os.path.exists(stamp):
+        have = open(stamp).read().split("\n")
+        # same sources; and the same flags unless the caller did not ask for a particular variant
+        # (LV_WATCHDOG unset: keep whichever variant was shipped, e.g. a watchdog build made before gpurun)
+        if have[0] == digest and ("LV_WATCHDOG" not in os.environ or have[1:2] == [flags]):
+            return LIB
     nvcc = _nvcc()
 
     def compile_one(src: str) -> str:
@@ -81,7 +91,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as f:
-        f.write(digest)
+        f.write(digest + "\n" + flags)
     return LIB
 
 

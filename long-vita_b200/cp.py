@@ -15,7 +15,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 from dataclasses import dataclass
-from typing import List, Optional
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -97,7 +97,89 @@ def _wrap_bf16(ptr: int, shape, device) -> torch.Tensor:
     return t.view(torch.bfloat16).view(*shape)
 
 
-class CPContext:
+class CPBackwardMixin:
+    """Backward of the context-parallel attention ("bwd ring for dKV"), first version:
+    a composition of the single-GPU backward kernels with two collectives of the CP group.
+
+      1. K/V of the whole sequence: all-gather of the ranks' local rows, re-ordered from zig-zag to
+         global order (`lv_row_gather`, bit-exact);
+      2. `lv_attn_bwd` on the local queries (two segments at their global positions) against the full
+         K/V: dQ is final; dK/dV are this rank's partial sums over the kv rows its queries see (the
+         kernel writes zeros for kv tiles no local query sees);
+      3. partial dK|dV rows re-ordered to rank-major zig-zag order and reduce-scattered to their owners.
+
+    The exchange volume per layer is 2 x S x hkv x d bf16 each way - under 1 % of the backward's run
+    time at the lengths context parallelism is used for (128K, cp 8: ~1 ms vs ~150 ms), which is why
+    this version uses the group's collectives instead of the forward's in-kernel pull.  Needs from the
+    host class: group, cp, rank, S, T, hkv, d."""
+
+    def _order(self, device):
+        if getattr(self, "_order_cache", None) is None or self._order_cache[0].device != torch.device(device):
+            order = torch.cat([zigzag_index(self.S, self.cp, r, device) for r in range(self.cp)])   # rank-major -> global pos
+            self._order_cache = (order, zigzag_unpermute_index(self.S, self.cp, device))
+        return self._order_cache
+
+    def gather_kv(self, k: torch.Tensor, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """k, v [T, hkv, d] local rows (zig-zag order) -> K, V [S, hkv, d] in global order."""
+        from . import ops
+
+        row = self.hkv * self.d
+        local = torch.cat([k.reshape(self.T, row), v.reshape(self.T, row)], dim=1).contiguous()     # [T, 2 row]
+        allr = torch.empty((self.cp * self.T, 2 * row), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(allr, local, group=self.group)
+        full = ops.row_gather(allr, self._order(local.device)[1])                                    # global order
+        return full[:, :row].view(self.S, self.hkv, self.d), full[:, row:].view(self.S, self.hkv, self.d)
+
+    def reduce_dkv(self, dk_partial: torch.Tensor, dv_partial: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """partials [S, hkv, d] (global order) -> this rank's summed rows [T, hkv, d] (zig-zag order)."""
+        from . import ops
+
+        row = self.hkv * self.d
+        part = torch.cat([dk_partial.reshape(self.S, row), dv_partial.reshape(self.S, row)], dim=1).contiguous()
+        by_rank = ops.row_gather(part, self._order(part.device)[0])                                  # [cp * T, 2 row]
+        mine = torch.empty((self.T, 2 * row), dtype=part.dtype, device=part.device)
+        dist.reduce_scatter_tensor(mine, by_rank, group=self.group)
+        return mine[:, :row].reshape(self.T, self.hkv, self.d), mine[:, row:].reshape(self.T, self.hkv, self.d)
+
+    def attention_backward(self, d_out, q, k, v, out, lse, scale: Optional[float] = None):
+        """d_out / q / out [T, hq, d], k / v [T, hkv, d] local rows, lse [1, hq, T] -> dq, dk, dv (local)."""
+        from . import ops
+
+        c = self.S // (2 * self.cp)
+        K, V = self.gather_kv(k, v)
+        dq, dk_p, dv_p = ops.attention_bwd(d_out.unsqueeze(0), q.unsqueeze(0), K.unsqueeze(0), V.unsqueeze(0),
+                                           out.unsqueeze(0), lse, causal=True, scale=scale, q_seg_len=c,
+                                           q_seg_pos=(self.rank * c, (2 * self.cp - 1 - self.rank) * c))
+        dk, dv = self.reduce_dkv(dk_p[0], dv_p[0])
+        return dq[0], dk, dv
+
+
+class _CPAttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, cp_ctx, scale):
+        out, lse = cp_ctx.attention_separate(q, k, v, scale=scale, return_lse=True)
+        T, hq, d = q.shape
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.cp_ctx, ctx.scale = cp_ctx, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, k, v, out, lse = ctx.saved_tensors
+        T, hq, d = q.shape
+        dq, dk, dv = ctx.cp_ctx.attention_backward(d_out.reshape(T, hq, d).contiguous(), q, k, v, out.view(T, hq, d), lse,
+                                                   scale=ctx.scale)
+        return dq, dk, dv, None, None
+
+
+def cp_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cp_ctx, scale: Optional[float] = None) -> torch.Tensor:
+    """Differentiable context-parallel causal attention: q [T, hq, d], k / v [T, hkv, d] are this
+    rank's zig-zag rows; returns [T, hq * d].  Forward = the fused in-kernel exchange
+    (`lv_attn_cp_fwd`), backward = CPBackwardMixin.attention_backward."""
+    return _CPAttentionFn.apply(q, k, v, cp_ctx, scale)
+
+
+class CPContext(CPBackwardMixin):
     """Per-process context-parallel state: two peer-mapped QKV buffers (epoch parity), the ready
     words, the local K/V staging buffers and block flags; peers' mappings opened via CUDA IPC."""
 
@@ -170,18 +252,22 @@ class CPContext:
         buf = self.qkv[self.epoch & 1]
         return self._launch(buf.data_ptr(), (self.T * self.row, self.row, self.d), out, scale)
 
-    def attention_separate(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out=None, scale=None):
+    def attention_separate(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out=None, scale=None,
+                           return_lse: bool = False):
         """q [T, hq, d], k/v [T, hkv, d] (strided views are fine): K|V are copied into the peer-mapped
-        buffer (T * 2 hkv d elements - small next to the attention itself), Q is read in place."""
+        buffer (T * 2 hkv d elements - small next to the attention itself), Q is read in place.
+        With return_lse also returns the log-sum-exp [1, hq, T] fp32 (what the backward needs)."""
         assert not self.fused_qkv
         buf = self.qkv[self.epoch & 1].view(self.T, 2, self.hkv, self.d)
         buf[:, 0].copy_(k)
         buf[:, 1].copy_(v)
         if q.stride(2) != 1 or q.stride(0) % 8 or q.stride(1) % 8:
             q = q.contiguous()
-        return self._launch(q.data_ptr(), (self.T * q.stride(0), q.stride(0), q.stride(1)), out, scale)
+        lse = torch.empty((1, self.hq, self.T), dtype=torch.float32, device=self.device) if return_lse else None
+        o = self._launch(q.data_ptr(), (self.T * q.stride(0), q.stride(0), q.stride(1)), out, scale, lse)
+        return (o, lse) if return_lse else o
 
-    def _launch(self, q_ptr, q_strides, out, scale):
+    def _launch(self, q_ptr, q_strides, out, scale, lse=None):
         from ._lib import AttnParams, CpParams
 
         T, hq, hkv, d = self.T, self.hq, self.hkv, self.d
@@ -190,7 +276,8 @@ class CPContext:
             out = torch.empty((T, hq * d), dtype=torch.bfloat16, device=self.device)
         c = self.S // (2 * self.cp)
         a = AttnParams()
-        a.q, a.k, a.v, a.out, a.lse = q_ptr, self.k_full.data_ptr(), self.v_full.data_ptr(), out.data_ptr(), None
+        a.q, a.k, a.v, a.out = q_ptr, self.k_full.data_ptr(), self.v_full.data_ptr(), out.data_ptr()
+        a.lse = None if lse is None else lse.data_ptr()
         a.batch, a.sq, a.sk, a.hq, a.hkv, a.d = 1, T, self.S, hq, hkv, d
         a.q_strides[0], a.q_strides[1], a.q_strides[2] = q_strides
         for arr in (a.k_strides, a.v_strides):
@@ -233,6 +320,8 @@ class ContextParallelRunner:
         self.cp = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.ctx: Optional[CPContext] = None
+        self.cache = None          # this rank's K/V cache shard after forward(..., use_cache=True)
+        self.total_len = 0         # tokens in the whole (sharded) cache
 
     def _context(self, S: int, device) -> CPContext:
         cfg = self.model.config
@@ -241,7 +330,7 @@ class ContextParallelRunner:
         return self.ctx
 
     def forward(self, input_ids: torch.Tensor, images: Optional[torch.Tensor], image_indices: Optional[torch.Tensor],
-                gather_logits: bool = True) -> torch.Tensor:
+                gather_logits: bool = True, use_cache: bool = False, max_new_tokens: int = 1024) -> torch.Tensor:
         """Every rank passes the FULL prompt (the reference broadcasts it, tasks/inference/module.py
         :340-356) and keeps its shard.  Returns the last-token logits [1, 1, vocab] on every rank."""
         from . import ops
@@ -259,9 +348,17 @@ class ContextParallelRunner:
                               sh.src_idx if feat is not None else None)
         cos, sin = ops.rope_table(sh.position_ids.to(torch.int64), m.inv_freq)
         T = x.shape[0]
+        self.cache = None
+        if use_cache:      # this rank's shard of the K/V cache: its T zig-zag rows + its share of the new tokens
+            from .kv_cache import KVCache
+
+            self.cache = KVCache(len(m.layers), T + -(-max_new_tokens // self.cp) + 1, cfg.num_key_value_heads, cfg.head_dim, dev)
+            self.total_len = S
         delta = None
-        for layer in m.layers:
-            x, delta = layer.forward_cp(x, delta, cos, sin, ctx)
+        for li, layer in enumerate(m.layers):
+            x, delta = layer.forward_cp(x, delta, cos, sin, ctx, self.cache, li)
+        if self.cache is not None:
+            self.cache.commit()
         h, _ = ops.rmsnorm(delta, m.norm_w, cfg.rms_norm_eps, residual=x)
         # logit mask: each rank projects its own last row; the globally-last token lives on rank 0
         # (chunk 2cp-1), generation.py:141-165
@@ -270,3 +367,36 @@ class ContextParallelRunner:
         if gather_logits:
             dist.broadcast(logits, src=dist.get_global_rank(self.group, 0), group=self.group)
         return logits
+
+    # -- incremental decoding over the sharded cache (SURVEY.md 8f-2 under context parallelism) --------------
+    def _merge(self, o_loc: torch.Tensor, lse_loc: torch.Tensor) -> torch.Tensor:
+        """Combine the ranks' partial attention results over their cache shards: out = sum_r w_r o_r with
+        w_r = exp(lse_r - logsumexp_r lse_r).  One all-gather of [hq, d + 1] floats (20 KB at 40 x 128)."""
+        hq, d = o_loc.shape
+        pack = torch.cat([o_loc.float(), lse_loc.view(hq, 1)], dim=1).contiguous()
+        allp = torch.empty((self.cp * hq, d + 1), dtype=torch.float32, device=pack.device)
+        dist.all_gather_into_tensor(allp, pack, group=self.group)
+        allp = allp.view(self.cp, hq, d + 1)
+        w = torch.softmax(allp[:, :, d], dim=0)                   # -inf (empty shard) -> weight 0
+        return (allp[:, :, :d] * w.unsqueeze(-1)).sum(dim=0).to(torch.bfloat16)
+
+    def decode(self, token: torch.Tensor) -> torch.Tensor:
+        """One generated token after forward(..., use_cache=True): every rank runs the token through the
+        (replicated) weights; attention reads only this rank's cache shard and the partial results are merged.
+        The new K/V row goes to rank `position % cp`.  Returns the logits [1, 1, vocab] (same on every rank)."""
+        from . import ops
+
+        m = self.model.model
+        cfg = self.model.config
+        assert self.cache is not None, "call forward(..., use_cache=True) first"
+        pos = self.total_len
+        owner = (pos % self.cp) == self.rank
+        x = ops.embed_scatter(token.view(1, 1), m.embed_tokens)
+        cos, sin = ops.rope_table(torch.tensor([pos], dtype=torch.int64, device=x.device), m.inv_freq)
+        delta = None
+        for li, layer in enumerate(m.layers):
+            x, delta = layer.forward(x, delta, cos, sin, {}, self.cache, li, shard_merge=self._merge, append=owner)
+        self.cache.commit()
+        self.total_len += 1
+        h, _ = ops.rmsnorm(delta, m.norm_w, cfg.rms_norm_eps, residual=x)
+        return ops.linear(h, self.model.lm_head).view(1, 1, -1)

@@ -21,6 +21,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -235,22 +237,26 @@ __global__ void __launch_bounds__(128, 1)
       mbar_wait(&str_full[stage], n_str[stage] & 1);
       ++n_str[stage];
       __syncthreads();   // column statistics of this stage are visible to every thread
-      // ---- MMA phase 1: the two SS GEMMs ----
-      if (tid == 0) {
+      // ---- MMA phase 1: the two SS GEMMs (warp 0, warp-uniform; one elected lane issues) ----
+      if (warp == 0) {
         tc_fence_after();
-        const uint32_t r0 = smem_u32(sR0), r1 = smem_u32(sR1);
-        const uint32_t s0 = smem_u32(sS0 + stage * TILE), s1 = smem_u32(sS1 + stage * TILE);
+        const uint64_t r0 = make_smem_desc(smem_u32(sR0), 16, 1024), r1 = make_smem_desc(smem_u32(sR1), 16, 1024);
+        const uint64_t s0 = make_smem_desc(smem_u32(sS0 + stage * TILE), 16, 1024);
+        const uint64_t s1 = make_smem_desc(smem_u32(sS1 + stage * TILE), 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
-          umma_ss(tA, make_smem_desc(r0 + off, 16, 1024), make_smem_desc(s0 + off, 16, 1024), idesc_ss, kk != 0);
-        }
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = ((kk / 4) * 16384 + (kk % 4) * 32) >> 4;
+            umma_ss(tA, r0 + off, s0 + off, idesc_ss, kk != 0);
+          }
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
-          umma_ss(tB, make_smem_desc(r1 + off, 16, 1024), make_smem_desc(s1 + off, 16, 1024), idesc_ss, kk != 0);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = ((kk / 4) * 16384 + (kk % 4) * 32) >> 4;
+            umma_ss(tB, r1 + off, s1 + off, idesc_ss, kk != 0);
+          }
+          umma_commit(mma1);
         }
-        umma_commit(mma1);
+        __syncwarp();
       }
       mbar_wait(mma1, n_mma1 & 1);
       ++n_mma1;
@@ -300,24 +306,28 @@ __global__ void __launch_bounds__(128, 1)
       tc_fence_before();
       __syncthreads();
 
-      // ---- MMA phase 2: TS GEMMs into the accumulators ----
-      if (tid == 0) {
+      // ---- MMA phase 2: TS GEMMs into the accumulators (warp 0, one elected lane issues) ----
+      if (warp == 0) {
         tc_fence_after();
-        const uint32_t s0 = smem_u32(sS0 + stage * TILE), s1 = smem_u32(sS1 + stage * TILE);
+        const uint64_t s0 = make_smem_desc(smem_u32(sS0 + stage * TILE), 16384, 1024);
+        const uint64_t s1 = make_smem_desc(smem_u32(sS1 + stage * TILE), 16384, 1024);
         const uint32_t acc = first ? 0u : 1u;
-        if (MODE == 0) {
+        if (elect_one()) {
+          if (MODE == 0) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dV += P^T dO
-            umma_ts(tAcc0, tA + kk * 8, make_smem_desc(s1 + kk * 2048, 16384, 1024), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
+            for (int kk = 0; kk < 8; ++kk)   // dV += P^T dO
+              umma_ts(tAcc0, tA + kk * 8, s1 + (uint64_t)(kk * 128), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dK += dS^T Q
-            umma_ts(tAcc1, tB + kk * 8, make_smem_desc(s0 + kk * 2048, 16384, 1024), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
-        } else {
+            for (int kk = 0; kk < 8; ++kk)   // dK += dS^T Q
+              umma_ts(tAcc1, tB + kk * 8, s0 + (uint64_t)(kk * 128), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
+          } else {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dQ += dS K
-            umma_ts(tAcc0, tB + kk * 8, make_smem_desc(s0 + kk * 2048, 16384, 1024), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
+            for (int kk = 0; kk < 8; ++kk)   // dQ += dS K
+              umma_ts(tAcc0, tB + kk * 8, s0 + (uint64_t)(kk * 128), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
+          }
+          umma_commit(mma2);
         }
-        umma_commit(mma2);
+        __syncwarp();
         // the streamed stage (and, for the next item, the resident tiles) may be overwritten only
         // after these MMAs have read them
         mbar_wait(mma2, n_mma2 & 1);
@@ -382,6 +392,382 @@ __global__ void __launch_bounds__(128, 1)
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// ================================================================================================
+// Version 2 of the backward kernel (LV_BWD_VERSION=2): the same two passes, warp-specialised and pipelined like
+// the forward v2 kernel.  Version 1 runs TMA wait -> MMA1 -> element-wise -> MMA2 strictly one after the other on
+// one warpgroup, so the tensor pipe idles through the whole element-wise phase (and vice versa).  Here
+//   warp 0      TMA producer (resident tiles per item, 128-row streamed tiles in a 2-stage ring, column statistics)
+//   warp 1      tcgen05 issuer
+//   warps 4-7   element-wise warpgroup 0 \  each streamed 128-row tile is consumed as two 64-row halves;
+//   warps 8-11  element-wise warpgroup 1 /  warpgroup b owns half b and the TMEM buffer pair b
+// TMEM: [S^T_0 | dP^T_0 | S^T_1 | dP^T_1] = 4 x 64 fp32 columns, accumulators at column 256 (D) and 256 + D (D).
+// The issuer queues MMA1 of half j+1 before it waits for the probabilities of half j, so S(j+1) is computed while
+// warpgroup j&1 is still in its exponentials, and MMA2(j) runs while warpgroup (j+1)&1 works.  Buffer reuse needs
+// no extra barrier: MMA1(j+2) is issued after MMA2(j) by the same thread, and tcgen05 operations of one thread
+// execute in order.  Arithmetic (masking, bf16 packing, MMA shapes of the TS products) is that of version 1.
+// ================================================================================================
+constexpr int B2_THREADS = 384;
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(B2_THREADS, 1)
+    attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                     const __grid_constant__ CUtensorMap tmOut0, const __grid_constant__ CUtensorMap tmOut1,
+                     const BwdKParams p) {
+  constexpr int TILE = 128 * D * 2;
+  constexpr int BOXES = D / 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sR0 = smem;                 // resident operand 0 (K or Q); staging of accumulator 0 in the epilogue
+  uint8_t* sR1 = sR0 + TILE;           // resident operand 1 (V or dO); staging of accumulator 1
+  uint8_t* sS0 = sR1 + TILE;           // streamed operand 0, 2 stages (Q or K)
+  uint8_t* sS1 = sS0 + 2 * TILE;       // streamed operand 1, 2 stages (dO or V)
+  float* s_lse = reinterpret_cast<float*>(sS1 + 2 * TILE);   // [2][128]  (MODE 0 only)
+  float* s_dlt = s_lse + 256;                               // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dlt + 256);
+  uint64_t* res_full = bars;          // resident tiles landed                 (tx, 1 arrival)
+  uint64_t* res_empty = bars + 1;     // both warpgroups' TMA stores have read the staging tiles (2 arrivals)
+  uint64_t* str_full = bars + 2;      // [2] streamed stage landed              (tx, 1 arrival)
+  uint64_t* str_empty = bars + 4;     // [2] both halves' MMA2 have read it     (tcgen05.commit)
+  uint64_t* s_full = bars + 6;        // [2] MMA1 of a half done                (tcgen05.commit)
+  uint64_t* p_full = bars + 8;        // [2] P^T / dS^T of a half written       (128 arrivals)
+  uint64_t* acc_full = bars + 10;     // all MMA2 of the item done              (tcgen05.commit / plain arrive)
+  uint64_t* acc_empty = bars + 11;    // accumulators read by the epilogue      (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmdO);
+    mbar_init(res_full, 1);
+    mbar_init(res_empty, 2);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&str_full[i], 1);
+      mbar_init(&str_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 256);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tAcc0 = tmem_base + 256;        // dV | dQ
+  const uint32_t tAcc1 = tmem_base + 256 + D;    // dK
+  const int G = p.hq / p.hkv;
+
+  // ---- the item / streamed-tile enumeration every role walks identically ----
+  struct Item {
+    int b, kvh, h_fixed, rt;
+  };
+  auto decode = [&](int item) {
+    Item w;
+    w.h_fixed = 0;
+    if (MODE == 0) {
+      w.rt = item % p.n_kt;
+      w.kvh = (item / p.n_kt) % p.hkv;
+      w.b = item / (p.n_kt * p.hkv);
+    } else {
+      const int r = item % p.n_qt;
+      w.rt = p.causal ? (p.n_qt - 1 - r) : r;
+      w.h_fixed = (item / p.n_qt) % p.hq;
+      w.kvh = w.h_fixed / G;
+      w.b = item / (p.n_qt * p.hq);
+    }
+    return w;
+  };
+  const int n_inner = (MODE == 0) ? G * p.n_qt : p.n_kt;
+  auto visible = [&](const Item& w, int it) -> bool {
+    if (MODE == 0) return pair_visible(p, it % p.n_qt, w.rt);
+    return pair_visible(p, w.rt, it);
+  };
+  auto next_visible = [&](const Item& w, int it) -> int {
+    while (it < n_inner && !visible(w, it)) ++it;
+    return it;
+  };
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    uint32_t item_cnt = 0, n_stream = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+      const Item w = decode(item);
+      mbar_wait(res_empty, (item_cnt & 1) ^ 1);           // previous item's epilogue has left the staging tiles
+      if (elect_one()) {
+        mbar_arrive_expect_tx(res_full, 2 * TILE);
+        for (int bx = 0; bx < BOXES; ++bx) {
+          if (MODE == 0) {
+            tma_load_4d(sR0 + bx * 16384, &tmK, res_full, bx * 64, w.rt * 128, w.kvh, w.b, kEvictFirst);
+            tma_load_4d(sR1 + bx * 16384, &tmV, res_full, bx * 64, w.rt * 128, w.kvh, w.b, kEvictFirst);
+          } else {
+            tma_load_4d(sR0 + bx * 16384, &tmQ, res_full, bx * 64, w.rt * 128, w.h_fixed, w.b, kEvictFirst);
+            tma_load_4d(sR1 + bx * 16384, &tmdO, res_full, bx * 64, w.rt * 128, w.h_fixed, w.b, kEvictFirst);
+          }
+        }
+      }
+      __syncwarp();
+      for (int it = next_visible(w, 0); it < n_inner; it = next_visible(w, it + 1), ++n_stream) {
+        const int st = n_stream & 1;
+        mbar_wait(&str_empty[st], ((n_stream >> 1) & 1) ^ 1);
+        if (MODE == 0) {
+          // column statistics of the 128 query rows of this tile (visible to the warpgroups through str_full)
+          const int qt = it % p.n_qt, h = w.kvh * G + it / p.n_qt;
+          for (int c = lane; c < 128; c += 32) {
+            const int qi = qt * 128 + c;
+            float l2 = INFINITY, dl = 0.f;
+            if (qi < p.sq) {
+              const long long o = ((long long)w.b * p.hq + h) * p.sq + qi;
+              l2 = p.lse[o] * 1.4426950408889634f;
+              dl = p.delta[o];
+            }
+            s_lse[st * 128 + c] = l2;
+            s_dlt[st * 128 + c] = dl;
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&str_full[st], 2 * TILE);
+          if (MODE == 0) {
+            const int qt = it % p.n_qt, h = w.kvh * G + it / p.n_qt;
+            for (int bx = 0; bx < BOXES; ++bx) {
+              tma_load_4d(sS0 + st * TILE + bx * 16384, &tmQ, &str_full[st], bx * 64, qt * 128, h, w.b, kEvictNormal);
+              tma_load_4d(sS1 + st * TILE + bx * 16384, &tmdO, &str_full[st], bx * 64, qt * 128, h, w.b, kEvictNormal);
+            }
+          } else {
+            for (int bx = 0; bx < BOXES; ++bx) {
+              tma_load_4d(sS0 + st * TILE + bx * 16384, &tmK, &str_full[st], bx * 64, it * 128, w.kvh, w.b, kEvictLast);
+              tma_load_4d(sS1 + st * TILE + bx * 16384, &tmV, &str_full[st], bx * 64, it * 128, w.kvh, w.b, kEvictLast);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc_ss = make_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_ts = make_idesc_bf16(128, D, 0, 1);
+    const uint64_t r0 = make_smem_desc(smem_u32(sR0), 16, 1024), r1 = make_smem_desc(smem_u32(sR1), 16, 1024);
+    uint32_t item_cnt = 0, n_stream = 0;
+    uint32_t pcnt[2] = {0, 0};
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+      const Item w = decode(item);
+      int nvis = 0;
+      for (int it = next_visible(w, 0); it < n_inner; it = next_visible(w, it + 1)) ++nvis;
+      const int J = 2 * nvis;                               // 64-row halves
+      mbar_wait(res_full, item_cnt & 1);
+      tc_fence_after();
+      auto stage_of = [&](int j) { return (int)((n_stream + (uint32_t)(j >> 1)) & 1); };
+      auto issue_mma1 = [&](int j) {
+        const int st = stage_of(j), h = j & 1;
+        if (h == 0) {
+          const uint32_t n = n_stream + (uint32_t)(j >> 1);
+          mbar_wait(&str_full[st], (n >> 1) & 1);
+          tc_fence_after();
+        }
+        const uint64_t s0 = make_smem_desc(smem_u32(sS0 + st * TILE) + h * 8192, 16, 1024);
+        const uint64_t s1 = make_smem_desc(smem_u32(sS1 + st * TILE) + h * 8192, 16, 1024);
+        const uint32_t tA = tmem_base + h * 128, tB = tmem_base + h * 128 + 64;
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = ((kk / 4) * 16384 + (kk % 4) * 32) >> 4;
+            umma_ss(tA, r0 + off, s0 + off, idesc_ss, kk != 0);
+          }
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = ((kk / 4) * 16384 + (kk % 4) * 32) >> 4;
+            umma_ss(tB, r1 + off, s1 + off, idesc_ss, kk != 0);
+          }
+          umma_commit(&s_full[h]);
+        }
+        __syncwarp();
+      };
+      if (J == 0) {
+        if (elect_one()) mbar_arrive(acc_full);             // nothing to accumulate: the epilogue writes zeros
+        __syncwarp();
+        continue;
+      }
+      issue_mma1(0);
+      for (int j = 0; j < J; ++j) {
+        if (j + 1 < J) issue_mma1(j + 1);
+        const int st = stage_of(j), h = j & 1;
+        mbar_wait(&p_full[h], pcnt[h] & 1);
+        ++pcnt[h];
+        if (j == 0) mbar_wait(acc_empty, (item_cnt & 1) ^ 1);   // previous item's accumulators have been read
+        tc_fence_after();
+        const uint64_t s0 = make_smem_desc(smem_u32(sS0 + st * TILE) + h * 8192, 16384, 1024);
+        const uint64_t s1 = make_smem_desc(smem_u32(sS1 + st * TILE) + h * 8192, 16384, 1024);
+        const uint32_t tA = tmem_base + h * 128, tB = tmem_base + h * 128 + 64;
+        const uint32_t acc = j > 0 ? 1u : 0u;
+        if (elect_one()) {
+          if (MODE == 0) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)   // dV += P^T dO      (K = 64 streamed rows)
+              umma_ts(tAcc0, tA + kk * 8, s1 + (uint64_t)(kk * 128), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)   // dK += dS^T Q
+              umma_ts(tAcc1, tB + kk * 8, s0 + (uint64_t)(kk * 128), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)   // dQ += dS K
+              umma_ts(tAcc0, tB + kk * 8, s0 + (uint64_t)(kk * 128), idesc_ts, (acc | (kk != 0)) ? 1u : 0u);
+          }
+          if (h == 1) umma_commit(&str_empty[st]);          // both halves of this stage have been consumed
+          if (j == J - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
+      }
+      n_stream += (uint32_t)nvis;
+    }
+  } else if (warp >= 4) {
+    // =========================== element-wise warpgroups + epilogue ===========================
+    const int b = (warp - 4) >> 2;                     // warpgroup = half index = TMEM buffer pair
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;                  // resident-tile row of this thread = TMEM lane
+    const uint32_t lane_base = uint32_t(quad * 32) << 16;
+    const uint32_t tA = tmem_base + lane_base + b * 128;
+    const uint32_t tB = tmem_base + lane_base + b * 128 + 64;
+    uint32_t item_cnt = 0, n_stream = 0, scnt = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_cnt) {
+      const Item w = decode(item);
+      float row_lse2 = INFINITY, row_delta = 0.f;
+      long long row_pos;
+      if (MODE == 1) {
+        const int qi = w.rt * 128 + row;
+        if (qi < p.sq) {
+          const long long o = ((long long)w.b * p.hq + w.h_fixed) * p.sq + qi;
+          row_lse2 = p.lse[o] * 1.4426950408889634f;
+          row_delta = p.delta[o];
+        }
+        row_pos = q_tile_pos(p, w.rt) + row;
+      } else {
+        row_pos = p.kv_pos0 + (long long)w.rt * 128 + row;
+      }
+      int nvis = 0;
+      for (int it = next_visible(w, 0); it < n_inner; it = next_visible(w, it + 1), ++nvis) {
+        const uint32_t n = n_stream + (uint32_t)nvis;
+        const int st = (int)(n & 1);
+        mbar_wait(&str_full[st], (n >> 1) & 1);        // acquires the column statistics the producer wrote
+        mbar_wait(&s_full[b], scnt & 1);
+        ++scnt;
+        tc_fence_after();
+        long long col_pos0;
+        int col_valid;
+        if (MODE == 0) {
+          const int qt = it % p.n_qt;
+          col_pos0 = q_tile_pos(p, qt) + b * 64;
+          col_valid = p.sq - qt * 128 - b * 64;
+        } else {
+          col_pos0 = p.kv_pos0 + (long long)it * 128 + b * 64;
+          col_valid = p.sk - it * 128 - b * 64;
+        }
+        const long long row0_pos = row_pos - row;
+        const bool need_mask = p.causal && (MODE == 0 ? (row0_pos + 127 > col_pos0) : (col_pos0 + 63 > row0_pos));
+#pragma unroll 1
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t sv[32], dv[32];
+          tmem_ld32(tA + c2 * 32, sv);
+          tmem_ld32(tB + c2 * 32, dv);
+          tmem_wait_ld();
+          uint32_t pp[16], ds[16];
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            float pv[2], dsv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = c2 * 32 + k + e;
+              const float l2 = (MODE == 0) ? s_lse[st * 128 + b * 64 + c] : row_lse2;
+              const float dl = (MODE == 0) ? s_dlt[st * 128 + b * 64 + c] : row_delta;
+              float pe = ex2(fmaf(__uint_as_float(sv[k + e]), p.scale_log2, -l2));
+              bool keep = c < col_valid;
+              if (need_mask) keep = keep && (MODE == 0 ? (row_pos <= col_pos0 + c) : (col_pos0 + c <= row_pos));
+              pe = keep ? pe : 0.f;
+              pv[e] = pe;
+              dsv[e] = pe * (__uint_as_float(dv[k + e]) - dl) * p.scale;
+            }
+            pp[k / 2] = pack_bf16(pv[0], pv[1]);
+            ds[k / 2] = pack_bf16(dsv[0], dsv[1]);
+          }
+          if (MODE == 0) tmem_st16(tA + c2 * 16, pp);
+          tmem_st16(tB + c2 * 16, ds);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[b]);
+      }
+      n_stream += (uint32_t)nvis;
+
+      // ---- epilogue: accumulator -> bf16 -> swizzled staging (the resident tile) -> TMA store ----
+      mbar_wait(acc_full, item_cnt & 1);
+      tc_fence_after();
+      const bool mine = (MODE == 0) || (b == 0);       // MODE 0: warpgroup b stores accumulator b; MODE 1: warpgroup 0
+      if (mine) {
+        uint8_t* stg = (b == 0 ? sR0 : sR1);
+        const uint32_t tacc = (b == 0 ? tAcc0 : tAcc1) + lane_base;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t o[32];
+          if (nvis > 0) {
+            tmem_ld32(tacc + c * 32, o);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o[k] = 0u;
+          }
+          uint8_t* box = stg + (c >> 1) * 16384 + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(o[8 * q + 0]), __uint_as_float(o[8 * q + 1]));
+            v.y = pack_bf16(__uint_as_float(o[8 * q + 2]), __uint_as_float(o[8 * q + 3]));
+            v.z = pack_bf16(__uint_as_float(o[8 * q + 4]), __uint_as_float(o[8 * q + 5]));
+            v.w = pack_bf16(__uint_as_float(o[8 * q + 6]), __uint_as_float(o[8 * q + 7]));
+            const int chunk = (c & 1) * 4 + q;
+            *reinterpret_cast<uint4*>(box + ((chunk ^ (row & 7)) << 4)) = v;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty);                          // every warpgroup thread, also the idle warpgroup of MODE 1
+      if (mine) {
+        fence_proxy_async_smem();
+        named_bar_sync(1 + b, 128);
+        if (quad == 0 && lane == 0) {
+          for (int bx = 0; bx < BOXES; ++bx) {
+            if (MODE == 0) {
+              if (b == 0) tma_store_4d(&tmOut0, sR0 + bx * 16384, bx * 64, w.rt * 128, w.kvh, w.b);   // dV
+              else tma_store_4d(&tmOut1, sR1 + bx * 16384, bx * 64, w.rt * 128, w.kvh, w.b);         // dK
+            } else {
+              tma_store_4d(&tmOut0, sR0 + bx * 16384, bx * 64, w.rt * 128, w.h_fixed, w.b);           // dQ
+            }
+          }
+          tma_store_commit();
+          tma_store_wait_read0();
+          mbar_arrive(res_empty);
+        }
+      } else if (quad == 0 && lane == 0) {
+        mbar_arrive(res_empty);
+      }
+    }
+    if (quad == 0 && lane == 0) tma_store_wait_all0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 static int make_map(CUtensorMap* m, const void* ptr, int64_t D, int64_t s, int64_t h, int64_t b, const int64_t* str) {
   const uint32_t box[4] = {64, 128, 1, 1};
   const uint64_t dims[4] = {(uint64_t)D, (uint64_t)s, (uint64_t)h, (uint64_t)b};
@@ -433,18 +819,31 @@ static int launch_bwd(const lv_attn_bwd_params* a, cudaStream_t s) {
   if (!attr_set) {
     LV_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     LV_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    LV_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    LV_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
+  // LV_BWD_VERSION=2: the warp-specialised, pipelined kernel (same arithmetic; see attn_bwd2_kernel)
+  static const int version = [] {
+    const char* e = getenv("LV_BWD_VERSION");
+    return (e != nullptr && e[0] == '2') ? 2 : 1;
+  }();
   {
     p.n_items = p.batch * p.hkv * p.n_kt;
     const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-    attn_bwd_kernel<D, 0><<<grid, 128, SMEM, s>>>(tmQ, tmK, tmV, tmdO, tmdV, tmdK, p);
+    if (version == 2)
+      attn_bwd2_kernel<D, 0><<<grid, B2_THREADS, SMEM, s>>>(tmQ, tmK, tmV, tmdO, tmdV, tmdK, p);
+    else
+      attn_bwd_kernel<D, 0><<<grid, 128, SMEM, s>>>(tmQ, tmK, tmV, tmdO, tmdV, tmdK, p);
     LV_CHECK_LAUNCH("attn_bwd_kernel<dKdV>");
   }
   {
     p.n_items = p.batch * p.hq * p.n_qt;
     const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-    attn_bwd_kernel<D, 1><<<grid, 128, SMEM, s>>>(tmQ, tmK, tmV, tmdO, tmdQ, tmdQ, p);
+    if (version == 2)
+      attn_bwd2_kernel<D, 1><<<grid, B2_THREADS, SMEM, s>>>(tmQ, tmK, tmV, tmdO, tmdQ, tmdQ, p);
+    else
+      attn_bwd_kernel<D, 1><<<grid, 128, SMEM, s>>>(tmQ, tmK, tmV, tmdO, tmdQ, tmdQ, p);
     LV_CHECK_LAUNCH("attn_bwd_kernel<dQ>");
   }
   return LV_OK;

@@ -45,6 +45,8 @@ struct AttnKParams {
   int n_qblk;      // ceil(sq / 256)
   int n_items;     // batch * hq * n_qblk
   int block_major; // 1: order work items (q-block, kv-head, head) - global longest-first; 0: (kv-head, q-block, head)
+  int serpentine;  // 1: odd rounds sweep the item list backwards (default); LV_ATTN_SCHED=0 turns it off for A/B runs
+  int poly_exp;    // 1: every 4th exponential of the softmax runs on the FMA pipe (polynomial), the rest on MUFU
   float* lse;
 };
 
@@ -93,6 +95,64 @@ __device__ __forceinline__ uint4 ld_peer_v4(const void* p) {
   return v;
 }
 
+// 2^x on the FMA pipe (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic minimax for 2^f
+// (max relative error 7.5e-5, tools/exp2_poly.py - 50x below the bf16 rounding P gets anyway), exponent
+// add through the low mantissa bits of the magic-number sum.  x is clamped to >= -125 so the result
+// stays a normal number (a masked -inf score becomes 2^-125 ~ 2e-38 instead of 0: invisible in l and P V).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;            // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.055171321f, f, 0.24261054f);
+  p = fmaf(p, f, 0.69326099f);
+  p = fmaf(p, f, 0.99992811f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// One 32-column chunk of a score row: P = 2^(S * scale_log2 - m), four partial row sums, bf16 pack.
+// POLY: every 4th exponential is evaluated on the FMA pipe (ex2_poly), relieving the MUFU pipe that both
+// softmax warpgroups share (16 ex2 / clk / SM = as many cycles as the two MMAs of a step at d = 128).
+template <bool POLY>
+__device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&sc)[32], float scale_log2, float neg_m, float& l0,
+                                                  float& l1, float& l2, float& l3, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float p0 = ex2(fmaf(__uint_as_float(sc[i + 0]), scale_log2, neg_m));
+    const float p1 = ex2(fmaf(__uint_as_float(sc[i + 1]), scale_log2, neg_m));
+    const float p2 = ex2(fmaf(__uint_as_float(sc[i + 2]), scale_log2, neg_m));
+    const float x3 = fmaf(__uint_as_float(sc[i + 3]), scale_log2, neg_m);
+    const float p3 = POLY ? ex2_poly(x3) : ex2(x3);
+    l0 += p0;
+    l1 += p1;
+    l2 += p2;
+    l3 += p3;
+    pk[i / 2] = pack_bf16(p0, p1);
+    pk[i / 2 + 1] = pack_bf16(p2, p3);
+  }
+}
+
+// LV_ATTN_POLY=1: softmax exponentials split 3:1 between MUFU (ex2.approx) and the FMA pipe.
+static int attn_poly_exp() {
+  static const int v = [] {
+    const char* e = getenv("LV_ATTN_POLY");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+  }();
+  return v;
+}
+
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Staging granularity: a 128-token key block is pulled as CP_SUB units of 32 tokens by different copier
+// warps, and blk_flags[b] COUNTS completed units (it reaches CP_SUB * (epoch + 1) when block b of this
+// epoch is whole).  With one unit per warp-visit and 8 x 16 B loads in flight per lane, a rank with few
+// blocks (short sequences) still keeps every copier warp of the grid and ~1.2 MB of NVLink reads in
+// flight; the first version moved one whole block per warp with 4 loads in flight and needed ~0.5 ms per
+// layer at 18K tokens / 8 ranks, all of it exposed.
+constexpr int CP_SUB = 4;
+constexpr int CP_UNIT_ROWS = A_BN / CP_SUB;
+
 __device__ __forceinline__ void cp_copier(const CpKParams& cpp, int warp, int lane) {
       const int cw = blockIdx.x * 2 + (warp - 2);          // copier index
       const int ncw = gridDim.x * 2;
@@ -105,48 +165,85 @@ __device__ __forceinline__ void cp_copier(const CpKParams& cpp, int warp, int la
       uint32_t seen = 1u << cpp.rank;                      // peers whose ready flag has been observed
       const int vec_per_row = cpp.kv_row_elems / 4;        // 16-byte vectors in one K|V row pair
       const int vec_per_half = cpp.kv_row_elems / 8;
-      for (int b = cw; b < cpp.nblk_needed; b += ncw) {
-        const int tok0 = b * A_BN;
+      const int n_units = cpp.nblk_needed * CP_SUB;
+      for (int u = cw; u < n_units; u += ncw) {
+        const int b = u / CP_SUB;
+        const int tok0 = b * A_BN + (u - b * CP_SUB) * CP_UNIT_ROWS;
         const int chunk = tok0 / cpp.chunk;
         const int owner = chunk < cpp.cp ? chunk : 2 * cpp.cp - 1 - chunk;
         const int lrow0 = (chunk < cpp.cp ? 0 : cpp.chunk) + (tok0 - chunk * cpp.chunk);
         if (!(seen & (1u << owner))) {
           if (lane == 0)
-            while (ld_acquire_sys(cpp.my_ready + owner) < cpp.epoch1) {
+            {
+              [[maybe_unused]] uint32_t spins = 0;
+              while (ld_acquire_sys(cpp.my_ready + owner) < cpp.epoch1) {
+                LV_SPIN_GUARD(spins, "peer ready word", cpp.my_ready + owner, cpp.epoch1)
+              }
             }
           __syncwarp();
           seen |= 1u << owner;
         }
         const __nv_bfloat16* src = cpp.peer_kv[owner] + (long long)lrow0 * cpp.peer_tok_stride;
-        const int total = A_BN * vec_per_row;
-        for (int i0 = 0; i0 < total; i0 += 32 * 4) {
-          uint4 v[4];
+        if (vec_per_row == 256) {
+          // K|V row pair = 4 KB (8 kv heads x 128): one row per warp pass, 8 loads in flight per lane,
+          // vectors 0..127 of the row are K, 128..255 are V
+          const __nv_bfloat16* s_lane = src + lane * 8;
+          __nv_bfloat16* dk = cpp.k_full + (long long)tok0 * cpp.kv_row_elems + lane * 8;
+          __nv_bfloat16* dv = cpp.v_full + (long long)tok0 * cpp.kv_row_elems + lane * 8;
+#pragma unroll 1
+          for (int row = 0; row < CP_UNIT_ROWS; ++row) {
+            uint4 v[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * 32 + lane;
-            const int row = i / vec_per_row, col = i - row * vec_per_row;
-            v[u] = ld_peer_v4(src + (long long)row * cpp.peer_tok_stride + col * 8);
+            for (int i = 0; i < 8; ++i) v[i] = ld_peer_v4(s_lane + i * 256);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              *reinterpret_cast<uint4*>(dk + i * 256) = v[i];
+              *reinterpret_cast<uint4*>(dv + i * 256) = v[4 + i];
+            }
+            s_lane += cpp.peer_tok_stride;
+            dk += cpp.kv_row_elems;
+            dv += cpp.kv_row_elems;
           }
+        } else {
+          const int total = CP_UNIT_ROWS * vec_per_row;
+          for (int i0 = 0; i0 < total; i0 += 32 * 4) {
+            uint4 v[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * 32 + lane;
-            const int row = i / vec_per_row, col = i - row * vec_per_row;
-            __nv_bfloat16* dst = col < vec_per_half
-                                     ? cpp.k_full + (long long)(tok0 + row) * cpp.kv_row_elems + col * 8
-                                     : cpp.v_full + (long long)(tok0 + row) * cpp.kv_row_elems + (col - vec_per_half) * 8;
-            *reinterpret_cast<uint4*>(dst) = v[u];
+            for (int k = 0; k < 4; ++k) {
+              const int i = i0 + k * 32 + lane;
+              const int row = i / vec_per_row, col = i - row * vec_per_row;
+              if (i < total) v[k] = ld_peer_v4(src + (long long)row * cpp.peer_tok_stride + col * 8);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int i = i0 + k * 32 + lane;
+              const int row = i / vec_per_row, col = i - row * vec_per_row;
+              if (i < total) {
+                __nv_bfloat16* dst = col < vec_per_half
+                                         ? cpp.k_full + (long long)(tok0 + row) * cpp.kv_row_elems + col * 8
+                                         : cpp.v_full + (long long)(tok0 + row) * cpp.kv_row_elems + (col - vec_per_half) * 8;
+                *reinterpret_cast<uint4*>(dst) = v[k];
+              }
+            }
           }
         }
+        // the staged rows are read by TMA (async proxy): order this lane's generic-proxy stores before the
+        // async proxy on the writer side as well (the producer fences again after its acquire)
+        fence_proxy_async_all();
         __threadfence();
         __syncwarp();
-        if (lane == 0) st_release_gpu(cpp.blk_flags + b, cpp.epoch1);
+        if (lane == 0) red_release_gpu_add(cpp.blk_flags + b, 1u);
       }
       if (cw == 0) {
         // do not retire before every peer has entered this epoch: a peer's flag for epoch e+1 then
         // proves it finished reading our epoch e-1 rows (buffer parity reuse)
         if (lane < cpp.cp && lane != cpp.rank)
+        {
+          [[maybe_unused]] uint32_t spins = 0;
           while (ld_acquire_sys(cpp.my_ready + lane) < cpp.epoch1) {
+            LV_SPIN_GUARD(spins, "peer epoch word (exit)", cpp.my_ready + lane, cpp.epoch1)
           }
+        }
         __syncwarp();
       }
 }
@@ -167,10 +264,10 @@ struct AttnCfg {
 // Static work assignment: the item list is sorted longest-first; CTAs sweep it boustrophedon (round r
 // forwards, round r+1 backwards) so every CTA receives a near-equal share of causal work without a
 // global atomic.  All warp roles of a CTA evaluate the same sequence.
-__device__ __forceinline__ int sched_item(int round, int n_items) {
+__device__ __forceinline__ int sched_item(int round, int n_items, int serpentine) {
   const int base = round * (int)gridDim.x;
   if (base >= n_items) return -1;
-  const int item = base + ((round & 1) ? ((int)gridDim.x - 1 - (int)blockIdx.x) : (int)blockIdx.x);
+  const int item = base + ((serpentine && (round & 1)) ? ((int)gridDim.x - 1 - (int)blockIdx.x) : (int)blockIdx.x);
   return item < n_items ? item : -1;
 }
 
@@ -298,7 +395,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     if (lane == 0) {
       uint32_t item_cnt = 0, kcnt = 0, vcnt = 0;
       int ready_upto = 0;   // CP: key blocks [0, ready_upto) are known to be staged
-      for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
+      for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
         const WorkItem w = decode_item(p, item);
         const int nmax = max(w.n[0], w.n[1]);
         for (int t = 0; t < 2; ++t) {
@@ -310,7 +407,11 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         }
         for (int j = 0; j < nmax; ++j) {
           if (CP && j >= ready_upto) {
-            while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1) {
+            {
+              [[maybe_unused]] uint32_t spins = 0;
+              while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1 * CP_SUB) {
+                LV_SPIN_GUARD(spins, "staged block flag", cpp.blk_flags + j, cpp.epoch1 * CP_SUB)
+              }
             }
             ready_upto = j + 1;
             fence_proxy_async_all();   // copier warps wrote the staging rows through the generic proxy
@@ -339,7 +440,12 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-    if (lane == 0) {
+    {
+      // The whole warp executes this warp-uniform control flow and ONE elected lane issues the
+      // tcgen05 instructions: descriptor arithmetic then lives in uniform registers.  (With the issue
+      // loop under `if (lane == 0)` the compiler wrapped every MMA in an ELECT / R2UR.BROADCAST /
+      // BRA.U.ANY sequence: ~73 issue cycles per 64-cycle MMA - the issuer was 64 % busy and bounded the
+      // kernel, profiles/README.md.)
       constexpr uint32_t idesc_qk = make_idesc_bf16(A_BM, A_BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(A_BM, D, 0, 1);
       const uint32_t tS[2] = {tmem_base + Cfg::TM_S0, tmem_base + Cfg::TM_S1};
@@ -347,18 +453,25 @@ __global__ void __launch_bounds__(A_THREADS, 1)
       uint32_t item_cnt = 0, kcnt = 0, vcnt_wait = 0, vcnt_rel = 0;
       uint32_t pcnt[2] = {0, 0};
 
+      // tiles are 1024-byte aligned, so stepping a descriptor is a plain add on its 14-bit address field
+      const uint64_t qdesc[2] = {make_smem_desc(smem_u32(sQ), 16, 1024), make_smem_desc(smem_u32(sQ + Cfg::TILE_BYTES), 16, 1024)};
+      const uint64_t kdesc0 = make_smem_desc(smem_u32(sK), 16, 1024);
+      const uint64_t vdesc0 = make_smem_desc(smem_u32(sV), 16384, 1024);
       auto issue_qk = [&](int t, int kst) {
-        const uint32_t qa = smem_u32(sQ + t * Cfg::TILE_BYTES);
-        const uint32_t ka = smem_u32(sK + kst * Cfg::TILE_BYTES);
+        const uint64_t qd = qdesc[t];
+        const uint64_t kd = kdesc0 + (uint64_t)((kst * Cfg::TILE_BYTES) >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
-          umma_ss(tS[t], make_smem_desc(qa + off, 16, 1024), make_smem_desc(ka + off, 16, 1024), idesc_qk,
-                  kk != 0 ? 1u : 0u);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = ((kk / 4) * 16384 + (kk % 4) * 32) >> 4;
+            umma_ss(tS[t], qd + off, kd + off, idesc_qk, kk != 0 ? 1u : 0u);
+          }
         }
+        __syncwarp();
       };
       auto issue_pv = [&](int t, int vst, bool accumulate) {
-        const uint32_t va = smem_u32(sV + vst * Cfg::TILE_BYTES);
+        const uint64_t vd = vdesc0 + (uint64_t)((vst * Cfg::TILE_BYTES) >> 4);
+        const bool leader = elect_one();
 #pragma unroll
         for (int kk = 0; kk < A_BN / 16; ++kk) {
           if (QH && (kk & 1) == 0) {
@@ -367,12 +480,16 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           }
           // A: P_t rows in TMEM, 16 bf16 (= 8 columns) per k-step.  B: V tile, MN-major: 16 key rows
           // (2 KB) per k-step, the second 64 head-dim columns live one 16 KB box further.
-          umma_ts(tO[t], tS[t] + kk * 8, make_smem_desc(va + kk * 2048, 16384, 1024), idesc_pv,
-                  (accumulate || kk != 0) ? 1u : 0u);
+          if (leader) umma_ts(tO[t], tS[t] + kk * 8, vd + (uint64_t)(kk * 128), idesc_pv, (accumulate || kk != 0) ? 1u : 0u);
         }
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
       };
 
-      for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
+      for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
         const WorkItem w = decode_item(p, item);
         const int n0 = w.n[0], n1 = w.n[1];
         const int nmax = max(n0, n1);
@@ -389,7 +506,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           }
           if (j < n0) {
             issue_qk(0, kst);
-            umma_commit(&s_full[0]);
+            commit(&s_full[0]);
           }
           if (j >= 1) {
             if (j - 1 < n1) {
@@ -402,18 +519,18 @@ __global__ void __launch_bounds__(A_THREADS, 1)
               ++pcnt[1];
               tc_fence_after();
               issue_pv(1, vc % NS, j - 1 > 0);
-              if (j - 1 == n1 - 1) umma_commit(&o_full[1]);
+              if (j - 1 == n1 - 1) commit(&o_full[1]);
             }
             // V(j-1) has now been consumed by every PV that needs it
-            umma_commit(&v_empty[vcnt_rel % NS]);
+            commit(&v_empty[vcnt_rel % NS]);
             ++vcnt_rel;
           }
           if (j < n1) {
             issue_qk(1, kst);
-            umma_commit(&s_full[1]);
+            commit(&s_full[1]);
           }
           if (j < nmax) {
-            umma_commit(&k_empty[kst]);
+            commit(&k_empty[kst]);
             ++kcnt;
           }
           if (j < n0) {
@@ -426,7 +543,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
             ++pcnt[0];
             tc_fence_after();
             issue_pv(0, vc % NS, j > 0);
-            if (j == n0 - 1) umma_commit(&o_full[0]);
+            if (j == n0 - 1) commit(&o_full[0]);
           }
         }
       }
@@ -444,7 +561,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     uint8_t* stage = sQ + t * Cfg::TILE_BYTES;
     uint32_t item_cnt = 0, scnt = 0, ocnt = 0;
 
-    for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
+    for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
       const WorkItem w = decode_item(p, item);
       const int n = w.n[t];
       const long long qpos = w.qpos[t] + row;           // global position of this thread's query row
@@ -516,19 +633,10 @@ __global__ void __launch_bounds__(A_THREADS, 1)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float p0 = ex2(fmaf(__uint_as_float(s[c][i + 0]), p.scale_log2, neg_m));
-            const float p1 = ex2(fmaf(__uint_as_float(s[c][i + 1]), p.scale_log2, neg_m));
-            const float p2 = ex2(fmaf(__uint_as_float(s[c][i + 2]), p.scale_log2, neg_m));
-            const float p3 = ex2(fmaf(__uint_as_float(s[c][i + 3]), p.scale_log2, neg_m));
-            l0 += p0;
-            l1 += p1;
-            l2 += p2;
-            l3 += p3;
-            pk[i / 2] = pack_bf16(p0, p1);
-            pk[i / 2 + 1] = pack_bf16(p2, p3);
-          }
+          if (p.poly_exp)
+            softmax_exp_chunk<true>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
+          else
+            softmax_exp_chunk<false>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
           tmem_st16(tS + c * 16, pk);
           if (QH) {
             tmem_wait_st();          // (also covers the lazy O rescale before the first quarter)
@@ -721,7 +829,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     if (lane == 0) {
       uint32_t item_cnt = 0, kcnt = 0, vcnt = 0;
       int ready_upto = 0;
-      for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
+      for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
         const WorkItem2 w = decode_item2(p, item);
         const int ntile = (max(w.n[0], w.n[1]) + 1) / 2;   // 128-row K/V tiles
         for (int t = 0; t < 2; ++t) {
@@ -733,7 +841,11 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         }
         for (int j = 0; j < ntile; ++j) {
           if (CP && j >= ready_upto) {
-            while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1) {
+            {
+              [[maybe_unused]] uint32_t spins = 0;
+              while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1 * CP_SUB) {
+                LV_SPIN_GUARD(spins, "staged block flag", cpp.blk_flags + j, cpp.epoch1 * CP_SUB)
+              }
             }
             ready_upto = j + 1;
             fence_proxy_async_all();
@@ -761,13 +873,13 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    {   // warp-uniform control flow; one elected lane issues (see the v1 kernel)
       constexpr uint32_t idesc_qk = make_idesc_bf16(A_BM, A_BH, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(A_BM, D, 0, 1);
       uint32_t item_cnt = 0;
       uint32_t kbase = 0, vbase = 0;            // ring counters of this item's tile 0
       uint32_t scnt[2][2] = {{0, 0}, {0, 0}};   // completed uses of s_full / p_full [tile][buffer]
-      for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
+      for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
         const WorkItem2 w = decode_item2(p, item);
         const int nmax = max(w.n[0], w.n[1]);
         const int ntile = (nmax + 1) / 2;
@@ -785,16 +897,18 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           }
           tc_fence_after();
           const int b = i & 1;
-          const uint32_t qa = smem_u32(sQ + t * Cfg::TILE_BYTES);
-          const uint32_t ka = smem_u32(sK + ((kbase + m) % NS) * Cfg::TILE_BYTES) + (i & 1) * 8192;
+          const uint64_t qd = make_smem_desc(smem_u32(sQ + t * Cfg::TILE_BYTES), 16, 1024);
+          const uint64_t kd = make_smem_desc(smem_u32(sK + ((kbase + m) % NS) * Cfg::TILE_BYTES) + (i & 1) * 8192, 16, 1024);
           const uint32_t d_tmem = tmem_base + t * 128 + b * 64;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
-            umma_ss(d_tmem, make_smem_desc(qa + off, 16, 1024), make_smem_desc(ka + off, 16, 1024), idesc_qk,
-                    kk != 0 ? 1u : 0u);
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint32_t off = ((kk / 4) * 16384 + (kk % 4) * 32) >> 4;
+              umma_ss(d_tmem, qd + off, kd + off, idesc_qk, kk != 0 ? 1u : 0u);
+            }
+            umma_commit(&s_full[t * 2 + b]);
           }
-          umma_commit(&s_full[t * 2 + b]);
+          __syncwarp();
         };
         auto issue_pv = [&](int t, int i) {
           const int m = i >> 1;
@@ -807,19 +921,25 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           mbar_wait(&p_full[t * 2 + b], scnt[t][b] & 1);
           ++scnt[t][b];
           tc_fence_after();
-          const uint32_t va = smem_u32(sV + ((vbase + m) % NS) * Cfg::TILE_BYTES) + (i & 1) * 8192;
+          const uint64_t vd = make_smem_desc(smem_u32(sV + ((vbase + m) % NS) * Cfg::TILE_BYTES) + (i & 1) * 8192, 16384, 1024);
           const uint32_t a_tmem = tmem_base + t * 128 + b * 64;
           const uint32_t d_tmem = tmem_base + 256 + t * D;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < A_BH / 16; ++kk)
-            umma_ts(d_tmem, a_tmem + kk * 8, make_smem_desc(va + kk * 2048, 16384, 1024), idesc_pv,
-                    (i > 0 || kk != 0) ? 1u : 0u);
-          umma_commit(&o_done[t]);
+            for (int kk = 0; kk < A_BH / 16; ++kk)
+              umma_ts(d_tmem, a_tmem + kk * 8, vd + (uint64_t)(kk * 128), idesc_pv, (i > 0 || kk != 0) ? 1u : 0u);
+            umma_commit(&o_done[t]);
+          }
+          __syncwarp();
         };
 
         for (int t = 0; t < 2; ++t)
           if (w.n[t] > 0) issue_qk(t, 0);
-        if (nmax == 1) umma_commit(&k_empty[kbase % NS]);
+        auto commit = [&](uint64_t* bar) {
+          if (elect_one()) umma_commit(bar);
+          __syncwarp();
+        };
+        if (nmax == 1) commit(&k_empty[kbase % NS]);
         for (int i = 0; i < nmax; ++i) {
           const int s = i + 1;
           // queue the next step's QK^T of both tiles first (they need no softmax result), so the
@@ -827,10 +947,10 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           if (s < w.n[0]) issue_qk(0, s);
           if (s < w.n[1]) issue_qk(1, s);
           if (s < nmax && ((s & 1) == 1 || s == nmax - 1))
-            umma_commit(&k_empty[(kbase + (s >> 1)) % NS]);   // last QK on this K tile has been issued
+            commit(&k_empty[(kbase + (s >> 1)) % NS]);   // last QK on this K tile has been issued
           if (i < w.n[0]) issue_pv(0, i);
           if (i < w.n[1]) issue_pv(1, i);
-          if ((i & 1) == 1 || i == nmax - 1) umma_commit(&v_empty[(vbase + (i >> 1)) % NS]);
+          if ((i & 1) == 1 || i == nmax - 1) commit(&v_empty[(vbase + (i >> 1)) % NS]);
         }
         kbase += ntile;
         vbase += ntile;
@@ -850,7 +970,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     uint32_t scnt[2] = {0, 0};   // uses of s_full[t][b]
     uint32_t pv_base = 0;        // PV commits on o_done[t] before this item
 
-    for (int round = 0, item; (item = sched_item(round, p.n_items)) >= 0; ++round, ++item_cnt) {
+    for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
       const WorkItem2 w = decode_item2(p, item);
       const int n = w.n[t];
       const long long qpos = w.qpos[t] + row;
@@ -911,19 +1031,10 @@ __global__ void __launch_bounds__(A_THREADS, 1)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t pk[16];
-#pragma unroll
-          for (int k = 0; k < 32; k += 4) {
-            const float p0 = ex2(fmaf(__uint_as_float(s[c][k + 0]), p.scale_log2, neg_m));
-            const float p1 = ex2(fmaf(__uint_as_float(s[c][k + 1]), p.scale_log2, neg_m));
-            const float p2 = ex2(fmaf(__uint_as_float(s[c][k + 2]), p.scale_log2, neg_m));
-            const float p3 = ex2(fmaf(__uint_as_float(s[c][k + 3]), p.scale_log2, neg_m));
-            l0 += p0;
-            l1 += p1;
-            l2 += p2;
-            l3 += p3;
-            pk[k / 2] = pack_bf16(p0, p1);
-            pk[k / 2 + 1] = pack_bf16(p2, p3);
-          }
+          if (p.poly_exp)
+            softmax_exp_chunk<true>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
+          else
+            softmax_exp_chunk<false>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
           tmem_st16(tS + b * 64 + c * 16, pk);
         }
         l += (l0 + l1) + (l2 + l3);
@@ -1048,6 +1159,12 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
   // all kv heads' K and V fit comfortably in the 126 MB L2 -> global longest-first order
   p.block_major = (a->causal && a->sk * a->hkv * a->d * 4 <= (64ll << 20)) ? 1 : 0;
   p.lse = a->lse;
+  p.poly_exp = attn_poly_exp();
+  static const int serp = [] {
+    const char* e = getenv("LV_ATTN_SCHED");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  p.serpentine = serp;
   static bool attr_set = false;
   if (!attr_set) {
     if constexpr (VER == 2) {
@@ -1126,7 +1243,6 @@ extern "C" int lv_attn_fwd(const lv_attn_params* a, lv_stream_t stream) {
 extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv_stream_t stream) {
   int rc = check_attn_params(a);
   if (rc) return rc;
-  LV_BIND_DEVICE(a->q);
   LV_CHECK_ARG(c != nullptr, "lv_attn_cp_fwd: null cp params");
   LV_CHECK_ARG(c->cp >= 2 && c->cp <= 8 && c->rank >= 0 && c->rank < c->cp, "lv_attn_cp_fwd: bad rank %d / cp %d", c->rank, c->cp);
   LV_CHECK_ARG(a->batch == 1 && a->causal, "lv_attn_cp_fwd: batch 1, causal only");
@@ -1156,6 +1272,7 @@ extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv
     k.peer_kv[p] = reinterpret_cast<const __nv_bfloat16*>(c->peer_kv[p]);
     k.peer_ready[p] = reinterpret_cast<uint32_t*>(c->peer_ready[p]) + parity * 8 + c->rank;
   }
+  LV_BIND_DEVICE(a->q);     // after every argument check, so that bad arguments are reported without touching CUDA
   k.my_ready = reinterpret_cast<const uint32_t*>(c->my_ready) + parity * 8;
   k.k_full = reinterpret_cast<__nv_bfloat16*>(c->k_full);
   k.v_full = reinterpret_cast<__nv_bfloat16*>(c->v_full);

@@ -131,6 +131,105 @@ __global__ void __launch_bounds__(256, 3) rmsnorm_kernel(const __nv_bfloat16* __
 }
 
 // ---------------------------------------------------------------------------------------------
+// RMSNorm backward.  Forward: y = bf16(x * rstd) * w with rstd = rsqrt(mean(x^2) + eps) (the bf16 rounding is
+// treated as the identity for the gradient, as autograd does through the reference's `.type_as(x)`).
+//   g = dy * w;   dx = rstd * (g - xhat * mean(g * xhat)) [+ add_in];   dw[j] = sum_rows dy[j] * xhat[j]
+// Each CTA walks rows with a grid stride and keeps its dw partial sums in registers; partial rows
+// [gridDim * RPC, cols] (fp32) are summed by the caller - no atomics, bit-reproducible.
+// ---------------------------------------------------------------------------------------------
+template <int TPR, int VPT>
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                          const __nv_bfloat16* __restrict__ w,
+                                                          const __nv_bfloat16* __restrict__ dy,
+                                                          const __nv_bfloat16* __restrict__ add_in,
+                                                          __nv_bfloat16* __restrict__ dx, float* __restrict__ dw_part,
+                                                          int64_t rows, int cols, float eps) {
+  constexpr int RPC = 256 / TPR;
+  __shared__ float red[RPC * (TPR > 32 ? TPR / 32 : 1)];
+  const int row_in_cta = threadIdx.x / TPR;
+  const int t = threadIdx.x % TPR;
+  const int nvec = cols / 8;
+  float dw_acc[VPT][8];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dw_acc[i][j] = 0.f;
+  for (int64_t base = (int64_t)blockIdx.x * RPC; base < rows; base += (int64_t)gridDim.x * RPC) {
+    const int64_t row = base + row_in_cta;
+    const bool row_ok = row < rows;
+    Vec8 xr[VPT], gr[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = t + i * TPR;
+      if (row_ok && c < nvec) {
+        xr[i] = ldg_stream(x + row * cols + c * 8);
+        gr[i] = ldg_stream(dy + row * cols + c * 8);
+      }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = t + i * TPR;
+      if (row_ok && c < nvec) {
+        float v[8];
+        unpack(xr[i], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
+      }
+    }
+    ss = row_reduce_sum<TPR>(ss, red, row_in_cta, t);
+    const float rstd = rsqrtf(ss / (float)cols + eps);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = t + i * TPR;
+      if (row_ok && c < nvec) {
+        float v[8], g[8], wv[8];
+        unpack(xr[i], v);
+        unpack(gr[i], g);
+        unpack(ldg_vec(w + c * 8), wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = v[j] * rstd;
+          dot += g[j] * wv[j] * xh;
+          dw_acc[i][j] += g[j] * xh;
+        }
+      }
+    }
+    dot = row_reduce_sum<TPR>(dot, red, row_in_cta, t) / (float)cols;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = t + i * TPR;
+      if (row_ok && c < nvec) {
+        float v[8], g[8], wv[8], o[8];
+        unpack(xr[i], v);
+        unpack(gr[i], g);
+        unpack(ldg_vec(w + c * 8), wv);
+        if (add_in != nullptr) {
+          float a[8];
+          unpack(ldg_stream(add_in + row * cols + c * 8), a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = rstd * (g[j] * wv[j] - v[j] * rstd * dot) + a[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = rstd * (g[j] * wv[j] - v[j] * rstd * dot);
+        }
+        stg_vec(dx + row * cols + c * 8, pack(o));
+      }
+    }
+  }
+  float* part = dw_part + ((int64_t)blockIdx.x * RPC + row_in_cta) * cols;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = t + i * TPR;
+    if (c < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part[c * 8 + j] = dw_acc[i][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // LayerNorm
 // ---------------------------------------------------------------------------------------------
 template <int TPR, int VPT>
@@ -280,6 +379,28 @@ __global__ void __launch_bounds__(256) swiglu_kernel(const __nv_bfloat16* __rest
   stg_vec(out + r * inter + c * 8, pack(o));
 }
 
+// d(gate|up) of h = silu(gate) * up:  dgate = dh * up * sig * (1 + gate * (1 - sig)),  dup = dh * silu(gate)
+__global__ void __launch_bounds__(256) swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu,
+                                                         const __nv_bfloat16* __restrict__ dh,
+                                                         __nv_bfloat16* __restrict__ dgu, int64_t rows, int64_t inter) {
+  const int64_t vpr = inter / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * vpr) return;
+  const int64_t r = idx / vpr, c = idx % vpr;
+  float g[8], u[8], d[8], og[8], ou[8];
+  unpack(ldg_stream(gu + r * 2 * inter + c * 8), g);
+  unpack(ldg_stream(gu + r * 2 * inter + inter + c * 8), u);
+  unpack(ldg_stream(dh + r * inter + c * 8), d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float sig = __fdividef(1.f, 1.f + __expf(-g[j]));
+    og[j] = d[j] * u[j] * sig * (1.f + g[j] * (1.f - sig));
+    ou[j] = d[j] * g[j] * sig;
+  }
+  stg_vec(dgu + r * 2 * inter + c * 8, pack(og));
+  stg_vec(dgu + r * 2 * inter + inter + c * 8, pack(ou));
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k = 0.7978845608028654f;
@@ -379,6 +500,28 @@ __global__ void __launch_bounds__(128) row_copy_kernel(const __nv_bfloat16* __re
 }
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Flash-decoding merge: one block per query head, one thread per head-dim column; every thread walks the
+// n_splits log-sum-exp values itself (n is ~18..150: cheaper than a block reduction).
+__global__ void __launch_bounds__(128) decode_merge_kernel(const __nv_bfloat16* __restrict__ o_part,
+                                                           const float* __restrict__ lse_part,
+                                                           __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out,
+                                                           int n, int G, int hkv, int d) {
+  const int kvh = blockIdx.x / G, g = blockIdx.x % G;
+  const int c = threadIdx.x;
+  float m = -INFINITY;
+  for (int s = 0; s < n; ++s) m = fmaxf(m, lse_part[((long long)s * hkv + kvh) * G + g]);
+  float sum = 0.f, acc = 0.f;
+  if (m > -INFINITY) {
+    for (int s = 0; s < n; ++s) {
+      const float w = __expf(lse_part[((long long)s * hkv + kvh) * G + g] - m);
+      sum += w;
+      if (c < d) acc = fmaf(w, __bfloat162float(o_part[(((long long)s * G + g) * hkv + kvh) * d + c]), acc);
+    }
+  }
+  if (c < d) out[((long long)kvh * G + g) * d + c] = __float2bfloat16_rn(sum > 0.f ? acc / sum : 0.f);
+  if (c == 0 && lse_out != nullptr) lse_out[kvh * G + g] = sum > 0.f ? m + __logf(sum) : -INFINITY;
+}
 
 }  // namespace lv
 
@@ -570,6 +713,71 @@ int lv_row_scatter_zero(const void* x, const int64_t* idx, void* out, int64_t n_
   if (n_idx == 0) return LV_OK;
   row_copy_kernel<<<(unsigned)n_idx, 128, 0, s>>>(BF(x), nullptr, idx, BFM(out), n_idx, cols, n_idx, n_rows_out);
   LV_CHECK_LAUNCH("row_copy_kernel(scatter_zero)");
+  return LV_OK;
+}
+
+int lv_attn_decode_merge(const void* o_part, const float* lse_part, void* out, float* lse_out, int64_t n_splits,
+                         int64_t group, int64_t hkv, int64_t d, lv_stream_t stream) {
+  LV_CHECK_ARG(o_part && lse_part && out, "lv_attn_decode_merge: null pointer");
+  LV_CHECK_ARG(n_splits > 0 && group > 0 && hkv > 0 && d > 0 && d <= 128, "lv_attn_decode_merge: bad shape");
+  LV_CHECK_ARG(n_splits < (1ll << 20) && group * hkv < (1ll << 20), "lv_attn_decode_merge: too large");
+  LV_BIND_DEVICE(o_part);
+  decode_merge_kernel<<<(unsigned)(group * hkv), 128, 0, (cudaStream_t)stream>>>(BF(o_part), lse_part, BFM(out), lse_out,
+                                                                            (int)n_splits, (int)group, (int)hkv, (int)d);
+  LV_CHECK_LAUNCH("decode_merge_kernel");
+  return LV_OK;
+}
+
+int64_t lv_rmsnorm_bwd_partials(int64_t rows, int64_t cols) {
+  // rows of the dw partial buffer the kernel writes: gridDim * rows-per-CTA (same TPR choice as the launch below)
+  const int64_t nvec = cols / 8;
+  const int tpr = nvec <= 32 * 4 ? 32 : (nvec <= 128 * 5 ? 128 : 256);
+  const int64_t rpc = 256 / tpr;
+  int64_t grid = (rows + rpc - 1) / rpc;
+  const int64_t cap = 2 * (int64_t)lv::sm_count();
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  return grid * rpc;
+}
+
+int lv_rmsnorm_bwd(const void* x, const void* w, const void* dy, const void* add_in, void* dx, float* dw_partials,
+                   int64_t rows, int64_t cols, float eps, lv_stream_t stream) {
+  LV_CHECK_ARG(x && w && dy && dx && dw_partials, "lv_rmsnorm_bwd: null pointer");
+  LV_CHECK_ARG(rows >= 0 && cols > 0 && cols % 8 == 0 && cols <= 16384, "lv_rmsnorm_bwd: cols=%lld must be a multiple of 8 and <= 16384", (long long)cols);
+  LV_CHECK_ARG(aligned16(x) && aligned16(w) && aligned16(dy) && aligned16(dx) && aligned16(add_in), "lv_rmsnorm_bwd: pointers must be 16-byte aligned");
+  LV_BIND_DEVICE(x);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t parts = lv_rmsnorm_bwd_partials(rows, cols);
+  if (rows == 0) {
+    LV_CHECK_CUDA(cudaMemsetAsync(dw_partials, 0, (size_t)parts * cols * 4, s));
+    return LV_OK;
+  }
+  const int nvec = (int)(cols / 8);
+#define LAUNCH_RMSB(TPR, VPT)                                                                                       \
+  rmsnorm_bwd_kernel<TPR, VPT><<<(unsigned)(parts / (256 / TPR)), 256, 0, s>>>(BF(x), BF(w), BF(dy), BF(add_in), BFM(dx), \
+                                                                                dw_partials, rows, (int)cols, eps)
+  if (nvec <= 32 * 4)
+    LAUNCH_RMSB(32, 4);
+  else if (nvec <= 128 * 4)
+    LAUNCH_RMSB(128, 4);
+  else if (nvec <= 128 * 5)
+    LAUNCH_RMSB(128, 5);
+  else
+    LAUNCH_RMSB(256, 8);
+#undef LAUNCH_RMSB
+  LV_CHECK_LAUNCH("rmsnorm_bwd_kernel");
+  return LV_OK;
+}
+
+int lv_swiglu_bwd(const void* gate_up, const void* dh, void* d_gate_up, int64_t rows, int64_t inter, lv_stream_t stream) {
+  LV_CHECK_ARG(gate_up && dh && d_gate_up, "lv_swiglu_bwd: null pointer");
+  LV_CHECK_ARG(inter > 0 && inter % 8 == 0, "lv_swiglu_bwd: inter=%lld must be a multiple of 8", (long long)inter);
+  LV_CHECK_ARG(aligned16(gate_up) && aligned16(dh) && aligned16(d_gate_up), "lv_swiglu_bwd: pointers must be 16-byte aligned");
+  if (rows == 0) return LV_OK;
+  LV_BIND_DEVICE(gate_up);
+  const int64_t total = rows * (inter / 8);
+  swiglu_bwd_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(BF(gate_up), BF(dh), BFM(d_gate_up), rows, inter);
+  LV_CHECK_LAUNCH("swiglu_bwd_kernel");
   return LV_OK;
 }
 

@@ -15,6 +15,7 @@
 // the nn.Linear calls of modeling_intern_vit.py:131,141,190-191 / resampler_projector.py:19-23.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -37,8 +38,7 @@ __device__ __forceinline__ float act_apply(float t, int act) {
   return t;
 }
 
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& mb, int& nb) {
-  constexpr int GM = 16;
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int GM, int& mb, int& nb) {
   const int per_group = GM * num_n;
   const int g = tile / per_group;
   const int first_m = g * GM;
@@ -51,7 +51,7 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int&
 __global__ void __launch_bounds__(G_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __nv_bfloat16* __restrict__ bias, int M, int N,
-                     int K, int act) {
+                     int K, int act, int gm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int mb, nb;
-        tile_coords(tile, num_m, num_n, mb, nb);
+        tile_coords(tile, num_m, num_n, gm, mb, nb);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], G_A_BYTES + G_B_BYTES);
@@ -115,8 +115,11 @@ __global__ void __launch_bounds__(G_THREADS, 1)
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
+    // warp-uniform control flow, one elected lane issues: descriptors stay in uniform registers
+    {
       constexpr uint32_t idesc = make_idesc_bf16(G_BM, G_BN, 0, 0);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -128,18 +131,22 @@ __global__ void __launch_bounds__(G_THREADS, 1)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * G_A_BYTES), 16, 1024);
-          const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * G_B_BYTES), 16, 1024);
+          const uint64_t adesc = adesc0 + (uint64_t)((stage * G_A_BYTES) >> 4);
+          const uint64_t bdesc = bdesc0 + (uint64_t)((stage * G_B_BYTES) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < G_BK / 16; ++kk)
-            umma_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+            for (int kk = 0; kk < G_BK / 16; ++kk)
+              umma_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+            umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          }
+          __syncwarp();
           if (++stage == G_STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&acc_full[as]);
+        if (elect_one()) umma_commit(&acc_full[as]);
+        __syncwarp();
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -156,7 +163,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
     uint32_t chunk_counter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int mb, nb;
-      tile_coords(tile, num_m, num_n, mb, nb);
+      tile_coords(tile, num_m, num_n, gm, mb, nb);
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       if (act == 3) {
@@ -325,6 +332,133 @@ __global__ void __launch_bounds__(128) add_cls_pos_kernel(const __nv_bfloat16* _
     out[tok * C + c] = __float2bfloat16_rn(__bfloat162float(src[c]) + __bfloat162float(pos[(int64_t)t * C + c]));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small-M path (decode: M = 1 new token, up to 4): the product is a weight stream - every W row is read
+// once, HBM-bound - and a 128x256 tensor-core tile would leave most SMs idle (N = 5120 -> 20 tiles).  One
+// warp owns two adjacent output columns (W rows r, r+1: the (gate, up) pair of the fused SwiGLU layout),
+// its lanes stride over K in 16-byte vectors with 4 loads in flight per row, fp32 accumulation, one
+// shuffle reduction.  Same epilogue arithmetic (bias, bf16 rounding before the activation, SwiGLU on
+// bf16-rounded gate / up) as the tensor-core kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ float dot8_bf16(const uint4& a, const uint4& b, float acc) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 af = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[i]));
+    const float2 bf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[i]));
+    acc = fmaf(af.x, bf.x, acc);
+    acc = fmaf(af.y, bf.y, acc);
+  }
+  return acc;
+}
+
+constexpr int GV_WARPS = 8, GV_UNROLL = 4;
+
+template <int MT>
+__global__ void __launch_bounds__(GV_WARPS * 32)
+    gemv_bf16_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W,
+                     const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ C, int M, int N, int K,
+                     long long lda, long long ldw, long long ldc, int act) {
+  const int lane = threadIdx.x & 31;
+  const long long r0 = 2ll * ((long long)blockIdx.x * GV_WARPS + (threadIdx.x >> 5));
+  if (r0 >= N) return;
+  const bool has1 = r0 + 1 < N;
+  const __nv_bfloat16* w0 = W + r0 * ldw;
+  const __nv_bfloat16* w1 = W + (has1 ? r0 + 1 : r0) * ldw;
+  float acc0[MT], acc1[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) acc0[m] = acc1[m] = 0.f;
+  for (int k0 = lane * 8; k0 < K; k0 += 256 * GV_UNROLL) {
+    uint4 a[GV_UNROLL], b[GV_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GV_UNROLL; ++u) {
+      const int k = k0 + u * 256;
+      if (k < K) {
+        a[u] = ld_stream_v4(w0 + k);
+        b[u] = ld_stream_v4(w1 + k);
+      } else {
+        a[u] = b[u] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < GV_UNROLL; ++u) {
+      const int k = k0 + u * 256;
+      if (k < K) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          if (m < M) {
+            const uint4 x = __ldg(reinterpret_cast<const uint4*>(A + m * lda + k));
+            acc0[m] = dot8_bf16(a[u], x, acc0[m]);
+            acc1[m] = dot8_bf16(b[u], x, acc1[m]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      acc0[m] += __shfl_xor_sync(0xffffffffu, acc0[m], off);
+      acc1[m] += __shfl_xor_sync(0xffffffffu, acc1[m], off);
+    }
+  }
+  if (lane != 0) return;
+  const float b0 = bias != nullptr ? __bfloat162float(bias[r0]) : 0.f;
+  const float b1 = (bias != nullptr && has1) ? __bfloat162float(bias[r0 + 1]) : 0.f;
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    if (m >= M) break;
+    float v0 = acc0[m] + b0, v1 = acc1[m] + b1;
+    if (act == 3) {   // (gate, up) pair -> one output column
+      const float g = __bfloat162float(__float2bfloat16_rn(v0)), up = __bfloat162float(__float2bfloat16_rn(v1));
+      C[m * ldc + r0 / 2] = __float2bfloat16_rn(__bfloat162float(__float2bfloat16_rn(__fdividef(g, 1.f + __expf(-g)))) * up);
+      continue;
+    }
+    if (act != 0) {
+      v0 = act_apply(__bfloat162float(__float2bfloat16_rn(v0)), act);
+      v1 = act_apply(__bfloat162float(__float2bfloat16_rn(v1)), act);
+    }
+    C[m * ldc + r0] = __float2bfloat16_rn(v0);
+    if (has1) C[m * ldc + r0 + 1] = __float2bfloat16_rn(v1);
+  }
+}
+
+// LV_GEMV=0 sends small-M products through the tensor-core kernel as well (A/B switch).
+static bool gemv_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LV_GEMV");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+
+static int launch_gemv(const void* A, const void* W, const void* bias, void* C, int64_t M, int64_t N, int64_t K,
+                       int64_t lda, int64_t ldw, int64_t ldc, int act, cudaStream_t s) {
+  const int64_t warps = (N + 1) / 2;
+  const unsigned grid = (unsigned)((warps + GV_WARPS - 1) / GV_WARPS);
+  const auto* a = reinterpret_cast<const __nv_bfloat16*>(A);
+  const auto* w = reinterpret_cast<const __nv_bfloat16*>(W);
+  const auto* b = reinterpret_cast<const __nv_bfloat16*>(bias);
+  auto* c = reinterpret_cast<__nv_bfloat16*>(C);
+  if (M == 1)
+    gemv_bf16_kernel<1><<<grid, GV_WARPS * 32, 0, s>>>(a, w, b, c, (int)M, (int)N, (int)K, lda, ldw, ldc, act);
+  else if (M == 2)
+    gemv_bf16_kernel<2><<<grid, GV_WARPS * 32, 0, s>>>(a, w, b, c, (int)M, (int)N, (int)K, lda, ldw, ldc, act);
+  else
+    gemv_bf16_kernel<4><<<grid, GV_WARPS * 32, 0, s>>>(a, w, b, c, (int)M, (int)N, (int)K, lda, ldw, ldc, act);
+  LV_CHECK_LAUNCH("gemv_bf16_kernel");
+  return LV_OK;
+}
+
 static int launch_gemm(const void* A, const void* W, const void* bias, void* C, int64_t M, int64_t N, int64_t K,
                        int64_t lda, int64_t ldw, int64_t ldc, int act, cudaStream_t s) {
   CUtensorMap tmA, tmB, tmC;
@@ -356,8 +490,16 @@ static int launch_gemm(const void* A, const void* W, const void* bias, void* C, 
   }
   const int64_t tiles = ((M + G_BM - 1) / G_BM) * ((N + G_BN - 1) / G_BN);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  // M-blocks per rasterisation group: the A panel of a group (gm x 128 rows x K) stays in L2 while its tiles sweep
+  // the N-blocks, and W is re-read from HBM once per group.  16 measured 969 MB of DRAM traffic on the QKV GEMM
+  // (476 MB algorithmic); LV_GEMM_GM=32 halves the W re-reads (A panel 42 MB at K = 5120, still L2-resident).
+  static const int gm = [] {
+    const char* e = getenv("LV_GEMM_GM");
+    const int v = e ? atoi(e) : 16;
+    return (v >= 1 && v <= 256) ? v : 16;
+  }();
   gemm_bf16_kernel<<<grid, G_THREADS, G_SMEM, s>>>(tmA, tmB, tmC, reinterpret_cast<const __nv_bfloat16*>(bias), (int)M,
-                                                   (int)N, (int)K, act);
+                                                   (int)N, (int)K, act, gm);
   LV_CHECK_LAUNCH("gemm_bf16_kernel");
   return LV_OK;
 }
@@ -380,6 +522,8 @@ int lv_gemm_bias_act(const void* A, const void* W, const void* bias, void* C, in
   LV_CHECK_ARG(act != 3 || (N % 16 == 0 && bias == nullptr), "lv_gemm_bias_act: fused SwiGLU needs N %% 16 == 0 and no bias");
   if (M == 0) return LV_OK;
   LV_BIND_DEVICE(A);
+  if (M <= 4 && gemv_enabled() && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0)
+    return launch_gemv(A, W, bias, C, M, N, K, lda, ldw, ldc, act, (cudaStream_t)stream);
   return launch_gemm(A, W, bias, C, M, N, K, lda, ldw, ldc, act, (cudaStream_t)stream);
 }
 

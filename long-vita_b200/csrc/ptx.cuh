@@ -6,6 +6,9 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#ifdef LV_WATCHDOG
+#include <cstdio>
+#endif
 
 namespace lv {
 
@@ -54,8 +57,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Debug builds (LV_WATCHDOG=1 at build time -> -DLV_WATCHDOG): a wait that spins for ~1 s of polling reports
+// which barrier of which warp is stuck and traps, so a protocol bug costs one error message instead of a hung GPU.
+#ifdef LV_WATCHDOG
+#define LV_SPIN_GUARD(n, what, addr, want)                                                                    \
+  if (++(n) > (1u << 24)) {                                                                                   \
+    printf("lv watchdog: %s stuck: block %d warp %d lane %d addr %p want %u\n", what, (int)blockIdx.x,         \
+           (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), (const void*)(addr), (unsigned)(want));           \
+    __trap();                                                                                                 \
+  }
+#else
+#define LV_SPIN_GUARD(n, what, addr, want)
+#endif
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  [[maybe_unused]] uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    LV_SPIN_GUARD(spins, "mbarrier", bar, parity)
   }
 }
 

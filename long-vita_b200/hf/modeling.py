@@ -6,10 +6,12 @@ composition of :90-221 (vision tower -> drop cls -> projector -> embedding gathe
 decoder layers -> final norm) and :309-311 (lm_head over the last `num_logits_to_keep` rows).
 All arithmetic runs in liblvb200.so (long_vita_b200.ops); PyTorch holds the buffers.
 
-Prefill only: `past_key_values` / `use_cache` are accepted for signature compatibility and must be
-empty / False (the Megatron serving path of the reference re-prefills every token,
-long_vita_megatron/inference/text_generation/generation.py:127-135; a KV-cache decode path is the
-next scope row).
+`use_cache=True` returns a `kv_cache.KVCache` in `past_key_values` (pre-allocated, post-RoPE rows); a
+later call with that cache and the new token(s) runs incremental decoding: one token -> the
+flash-decoding composition `ops.attention_decode`, several tokens -> the fused kernel with the
+bottom-right-aligned causal mask over cache + new rows (chunked prefill).  Images are encoded only when
+the cache is empty (modeling_long_vita.py:90).  The Megatron serving path of the reference re-prefills
+every token (long_vita_megatron/inference/text_generation/generation.py:127-135); SURVEY.md 8f-2.
 """
 from __future__ import annotations
 
@@ -20,6 +22,7 @@ import torch
 
 from .. import ops
 from ..config import LongVITAConfig
+from ..kv_cache import KVCache
 
 
 @dataclass
@@ -130,9 +133,11 @@ class DecoderLayer:
         self.ln1 = w[p + "input_layernorm.weight"]
         self.ln2 = w[p + "post_attention_layernorm.weight"]
 
-    def forward(self, x: torch.Tensor, delta: Optional[torch.Tensor], cos, sin, attn_kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+    def forward(self, x: torch.Tensor, delta: Optional[torch.Tensor], cos, sin, attn_kwargs, cache=None,
+                layer_idx: int = 0, shard_merge=None, append: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
         """x [T, H] residual stream, `delta` the previous layer's MLP output not yet added
-        (the add is fused into this layer's first RMSNorm).  Returns (x, delta)."""
+        (the add is fused into this layer's first RMSNorm).  Returns (x, delta).  With `cache` the new
+        K/V rows are appended to it and attention runs over cache + new rows."""
         cfg = self.cfg
         T = x.shape[0]
         hq, hkv, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
@@ -146,13 +151,35 @@ class DecoderLayer:
         v = qkv[:, (hq + hkv) * d :].view(T, hkv, d)
         ops.rope(q, cos, sin, out=q)
         ops.rope(k, cos, sin, out=k)
-        att = ops.attention_fwd(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), causal=True, **attn_kwargs)
-        o = ops.linear(att.view(T, hq * d), self.wo)
+        if cache is None:
+            att = ops.attention_fwd(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), causal=True, **attn_kwargs)
+        elif T == 1 and shard_merge is not None:
+            # context-parallel decode: the cache is sharded over the ranks (any split of the keys works for a
+            # query that sees them all); this rank attends over its shard, `shard_merge` combines the ranks'
+            # (out, lse) pairs.  Only the rank that owns the new position appends its K/V row.
+            if append:
+                kc, vc, length = cache.append(layer_idx, k, v)
+            else:
+                kc, vc, length = cache.k[layer_idx], cache.v[layer_idx], len(cache)
+            if length > 0:
+                o_loc, lse_loc = ops.attention_decode(q[0], kc, vc, length, return_lse=True)
+            else:
+                o_loc = torch.zeros((hq, d), dtype=torch.bfloat16, device=x.device)
+                lse_loc = torch.full((hq,), float("-inf"), dtype=torch.float32, device=x.device)
+            att = shard_merge(o_loc, lse_loc)
+        else:
+            kc, vc, length = cache.append(layer_idx, k, v)
+            if T == 1:
+                att = ops.attention_decode(q[0], kc, vc, length)
+            else:      # first prefill (empty cache) or a chunk of new tokens: causal, aligned to the last key
+                att = ops.attention_fwd(q.unsqueeze(0), kc[:length].unsqueeze(0), vc[:length].unsqueeze(0), causal=True)
+        o = ops.linear(att.reshape(T, hq * d), self.wo)
         h, x = ops.rmsnorm(o, self.ln2, cfg.rms_norm_eps, residual=x)
         a = ops.linear(h, self.w_gate_up, act="swiglu")
         return x, ops.linear(a, self.w_down)
 
-    def forward_cp(self, x: torch.Tensor, delta: Optional[torch.Tensor], cos, sin, ctx) -> Tuple[torch.Tensor, torch.Tensor]:
+    def forward_cp(self, x: torch.Tensor, delta: Optional[torch.Tensor], cos, sin, ctx, cache=None,
+                   layer_idx: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
         """The same layer on this rank's zig-zag shard (`ctx` is the rank's cp.CPContext): the QKV GEMM
         writes straight into the peer-mapped buffer, RoPE runs in place there, and the fused kernel
         pulls the other ranks' K/V itself (lv_attn_cp_fwd)."""
@@ -168,6 +195,8 @@ class DecoderLayer:
         k = qkv[:, hq * d : (hq + hkv) * d].view(T, hkv, d)
         ops.rope(q, cos, sin, out=q)
         ops.rope(k, cos, sin, out=k)
+        if cache is not None:      # this rank's zig-zag rows become its shard of the K/V cache
+            cache.append(layer_idx, k, qkv[:, (hq + hkv) * d :].view(T, hkv, d))
         o = ops.linear(ctx.attention(), self.wo)
         h, x = ops.rmsnorm(o, self.ln2, cfg.rms_norm_eps, residual=x)
         a = ops.linear(h, self.w_gate_up, act="swiglu")
@@ -186,6 +215,7 @@ class LongVITAModel:
         self.inv_freq = (1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.int64).float()
                                                     / cfg.head_dim))).to(self.embed_tokens.device)
         self.vision_chunk = 256  # frames per ViT pass (pretrain_long_vita.py:522-533)
+        self.default_new_tokens = 1024   # head-room of a cache created by use_cache=True (max_cache_len= overrides)
 
     def encode_images(self, images: torch.Tensor) -> torch.Tensor:
         feats = []
@@ -213,17 +243,18 @@ class LongVITAModel:
         cfg = self.config
         if (input_ids is None) ^ (inputs_embeds is not None):
             raise ValueError("You must specify exactly one of input_ids or inputs_embeds")
-        if past_key_values is not None and len(past_key_values) != 0:
-            raise NotImplementedError("KV-cache decode is out of this build's scope (prefill forward only)")
-        if use_cache:
-            raise NotImplementedError("use_cache=True is not supported (prefill forward only)")
+        if past_key_values is not None and not isinstance(past_key_values, KVCache):
+            if len(past_key_values) != 0:
+                raise NotImplementedError("past_key_values must be the KVCache returned by a use_cache=True call")
+            past_key_values = None
         if output_attentions:
             raise NotImplementedError("attention probabilities are never materialised by the fused kernel")
         if attention_mask is not None and not bool(attention_mask.to(torch.bool).all()):
             raise NotImplementedError("padding masks are not supported; pass unpadded sequences (batch 1)")
 
+        past_len = 0 if past_key_values is None else past_key_values.get_seq_length()
         image_embeds = None
-        if images is not None:
+        if images is not None and past_len == 0:                  # modeling_long_vita.py:90
             image_embeds = self.encode_images(images)
             assert image_embeds.shape[0] == len(images)
 
@@ -243,18 +274,25 @@ class LongVITAModel:
                 raise NotImplementedError("batch size 1")
             x = inputs_embeds.reshape(s, -1).contiguous()
 
+        cache = past_key_values
+        if use_cache and cache is None:
+            capacity = int(flash_attn_kwargs.pop("max_cache_len", 0)) or s + self.default_new_tokens
+            cache = KVCache(len(self.layers), capacity, cfg.num_key_value_heads, cfg.head_dim, x.device)
+        flash_attn_kwargs.pop("max_cache_len", None)
         if cache_position is None:
-            cache_position = torch.arange(0, s, device=x.device)
+            cache_position = torch.arange(past_len, past_len + s, device=x.device)     # modeling_long_vita.py:153-158
         if position_ids is None:
             position_ids = cache_position.unsqueeze(0)
         cos, sin = ops.rope_table(position_ids.reshape(-1).to(torch.int64), self.inv_freq)
 
         all_hidden = () if output_hidden_states else None
         delta = None
-        for layer in self.layers:
+        for li, layer in enumerate(self.layers):
             if output_hidden_states:
                 all_hidden += ((x if delta is None else x + delta).view(1, s, -1),)
-            x, delta = layer.forward(x, delta, cos, sin, {})
+            x, delta = layer.forward(x, delta, cos, sin, {}, cache, li)
+        if cache is not None:
+            cache.commit()
         if delta is None:
             h = ops.rmsnorm(x, self.norm_w, cfg.rms_norm_eps)
         else:
@@ -262,7 +300,7 @@ class LongVITAModel:
         h = h.view(1, s, -1)
         if output_hidden_states:
             all_hidden += (h,)
-        out = BaseOutput(last_hidden_state=h, past_key_values=None, hidden_states=all_hidden)
+        out = BaseOutput(last_hidden_state=h, past_key_values=cache, hidden_states=all_hidden)
         return out if (return_dict is None or return_dict) else out.to_tuple()
 
     __call__ = forward
@@ -297,6 +335,7 @@ class LongVITAForCausalLM:
         model.inv_freq = (1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.int64).float()
                                                      / cfg.head_dim))).to(device)
         model.vision_chunk = 256
+        model.default_new_tokens = 1024
         model.layers = []
         for i in range(n_layers):
             lw = llm_layer_weights(cfg, i, seed, device, torch.bfloat16, perturb)
@@ -338,7 +377,31 @@ class LongVITAForCausalLM:
             # loss_function of transformers (shifted CE in fp32); host-side torch, off the hot path
             lg = logits.float()[:, :-1].reshape(-1, logits.shape[-1])
             loss = torch.nn.functional.cross_entropy(lg, labels[:, -logits.shape[1]:][:, 1:].reshape(-1), ignore_index=-100)
-        out = CausalLMOutput(loss=loss, logits=logits, past_key_values=None, hidden_states=outputs.hidden_states)
+        out = CausalLMOutput(loss=loss, logits=logits, past_key_values=outputs.past_key_values,
+                             hidden_states=outputs.hidden_states)
         return out if (return_dict is None or return_dict) else out.to_tuple()
 
     __call__ = forward
+
+    @torch.no_grad()
+    def generate_greedy(self, input_ids: torch.Tensor, images: Optional[torch.Tensor] = None,
+                        image_indices: Optional[torch.Tensor] = None, max_new_tokens: int = 16,
+                        eos_token_id: Optional[int] = None) -> torch.Tensor:
+        """Greedy decoding with the K/V cache: one prefill, then one forward per token over a single new
+        row (the reference's Megatron loop feeds the whole sequence again for every token,
+        generation.py:127-135).  Returns the generated ids [1, n]."""
+        s = input_ids.shape[1]
+        out = self.forward(input_ids=input_ids, images=images, image_indices=image_indices, use_cache=True,
+                           num_logits_to_keep=1, max_cache_len=s + max_new_tokens)
+        cache = out.past_key_values
+        new = []
+        tok = out.logits[0, -1].float().argmax().view(1, 1)
+        for _ in range(max_new_tokens):
+            new.append(tok)
+            if eos_token_id is not None and int(tok) == eos_token_id:
+                break
+            if len(new) == max_new_tokens:
+                break
+            out = self.forward(input_ids=tok, past_key_values=cache, use_cache=True, num_logits_to_keep=1)
+            tok = out.logits[0, -1].float().argmax().view(1, 1)
+        return torch.cat(new, dim=1)

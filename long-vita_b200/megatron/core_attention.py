@@ -44,7 +44,12 @@ def _attention_sbhd(query, key, value, causal: bool, scale: float, cp_ctx=None):
     if cp_ctx is not None:
         if b != 1:
             raise AssertionError("context-parallel attention supports micro-batch 1 (the reference's long-context setting)")
-        out = cp_ctx.attention_separate(query[:, 0], key[:, 0], value[:, 0], scale=scale)   # [sq, np*hn]
+        if torch.is_grad_enabled() and (query.requires_grad or key.requires_grad or value.requires_grad):
+            from ..cp import cp_attention      # training: fused exchange forward + lv_attn_bwd / reduce-scatter backward
+
+            out = cp_attention(query[:, 0], key[:, 0], value[:, 0], cp_ctx, scale)
+        else:
+            out = cp_ctx.attention_separate(query[:, 0], key[:, 0], value[:, 0], scale=scale)   # [sq, np*hn]
         return out.view(sq, 1, np_ * hn)
     if torch.is_grad_enabled() and (query.requires_grad or key.requires_grad or value.requires_grad):
         # training: differentiable path (lv_attn_bwd through torch.autograd.Function)

@@ -8,8 +8,10 @@ return (:379).  The state dict is the Megatron-core (TE-spec) one - see `checkpo
 
 What is kept from the reference and what is deliberately not:
 * `inference_params.external_inputs` / `.logit_mask` overrides (:268-272, :287-289) and
-  `use_kv_cache == False -> inference_params = None` (:291-292) are honoured; a live KV cache raises
-  (prefill only - the reference's own serving loop re-prefills every token, generation.py:127-135).
+  `use_kv_cache == False -> inference_params = None` (:291-292) are honoured.  With a live `inference_params`
+  (Megatron's `--use-kv-cache` protocol, generation.py:127-131: only the new tokens are passed) the K/V rows go
+  to a pre-allocated `kv_cache.KVCache` kept in `inference_params.key_value_memory_dict` and a single new token
+  runs the flash-decoding path.
 * `hidden_states += 0.0 * self.unused` (:310-311) is an exact no-op on finite values and only exists
   to keep an otherwise unused parameter in the autograd graph; not executed.
 * labels: `masked_select(labels, logit_mask)` (:389-391), the `is_instruction_dataset` shift
@@ -143,23 +145,40 @@ class B200GPTVLModel:
             logit_mask = inference_params.logit_mask
         if hasattr(inference_params, "use_kv_cache") and not inference_params.use_kv_cache:
             inference_params = None
-        if inference_params is not None and getattr(inference_params, "key_value_memory_dict", None):
-            raise NotImplementedError("KV-cache decode is outside this build's scope (prefill forward only)")
+        # Megatron's incremental decoding protocol (`--use-kv-cache`, generation.py:127-131): the caller passes only
+        # the new tokens and their positions; per-layer K/V live in `inference_params.key_value_memory_dict`.  Here
+        # that dict holds one pre-allocated kv_cache.KVCache for the whole model.
+        cache = None
+        if inference_params is not None:
+            if self.cp is not None:
+                raise NotImplementedError("KV-cache decoding under context parallelism goes through "
+                                          "cp.ContextParallelRunner (sharded cache)")
+            from ..kv_cache import KVCache
+
+            kv = inference_params.key_value_memory_dict
+            cache = kv.get("b200_kv_cache")
+            if cache is None:
+                capacity = int(getattr(inference_params, "max_sequence_length", 0) or (s + 1024))
+                cache = KVCache(len(self.layers), capacity, cfg.num_key_value_heads, cfg.head_dim, x.device)
+                kv["b200_kv_cache"] = cache
 
         # RoPE: Megatron builds the table for positions 0..S-1 and slices it zig-zag under CP
         # (rotary_pos_embedding.py:36-47, 84-122); position_ids from get_batch_on_this_cp_rank are
         # exactly those positions, so the table is generated from them directly.
         if position_ids is None:
             assert self.cp is None, "context parallelism needs this rank's position_ids"
-            position_ids = torch.arange(s, device=x.device).unsqueeze(0)
+            p0 = 0 if cache is None else len(cache)
+            position_ids = torch.arange(p0, p0 + s, device=x.device).unsqueeze(0)
         cos, sin = ops.rope_table(position_ids.reshape(-1).to(torch.int64), self.inv_freq)
 
         delta = None
-        for layer in self.layers:
+        for li, layer in enumerate(self.layers):
             if self.cp is None:
-                x, delta = layer.forward(x, delta, cos, sin, {})
+                x, delta = layer.forward(x, delta, cos, sin, {}, cache, li)
             else:
                 x, delta = layer.forward_cp(x, delta, cos, sin, self.cp)
+        if cache is not None:
+            cache.commit()
         if delta is None:
             h = ops.rmsnorm(x, self.final_layernorm, cfg.rms_norm_eps)
         else:

@@ -21,8 +21,9 @@ tools/hf2mcore_long_vita.py:486-507):
 then its k, then its v; hf2mcore_long_vita.py:488-498); it is re-ordered once, lazily, into
 [all q | all k | all v] so that q/k/v are uniformly strided views of one GEMM output.
 
-Forward only in this round (prefill / serving); training through this module needs the GEMM and
-token-wise backward kernels, which are the next scope row.
+Inference takes the fused path (GEMM epilogues, in-place RoPE, fused add + norm).  When gradients are enabled and
+anything requires grad, `_forward_train` builds the same layer from differentiable pieces whose backward passes are
+kernels too (`lv_rmsnorm_bwd`, `lv_swiglu_bwd`, `lv_attn_bwd`, the GEMM on transposed operands).
 """
 from __future__ import annotations
 
@@ -108,6 +109,8 @@ class B200TransformerLayer(torch.nn.Module):
         s, b, h = hidden_states.shape
         if b != 1:
             raise NotImplementedError("micro-batch 1 (the reference's long-context setting)")
+        if torch.is_grad_enabled() and (hidden_states.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self._forward_train(hidden_states, rotary_pos_emb), context
         if self._qkv_w is None:
             self._ungroup()
         np_, ng, hn = self.np, self.ng, self.hn
@@ -128,6 +131,36 @@ class B200TransformerLayer(torch.nn.Module):
         d = ops.linear(a, self.mlp.linear_fc2.weight)
         out = ops.ls_residual(x, d)           # plain residual add (bias-dropout-add with p = 0, no bias)
         return out.view(s, b, h), context
+
+
+    # -- training: the same layer out of differentiable pieces (ops.*_autograd) --------------------------------
+    def _forward_train(self, hidden_states, rotary_pos_emb):
+        """Forward that records an autograd graph: every operator is a torch.autograd.Function over the C-ABI kernels
+        (RMSNorm / SwiGLU / RoPE backward kernels, `lv_attn_bwd`, and the tcgen05 GEMM for dX and dW).  It works on the
+        Megatron parameter layouts directly (grouped QKV rows, fc1 = cat(gate, up)), so gradients land on the
+        parameters Megatron's optimizer owns; the fused-epilogue / in-place shortcuts of the inference path are not
+        used here (the un-fused gate|up activation is what the SwiGLU backward needs)."""
+        s, b, h = hidden_states.shape
+        np_, ng, hn = self.np, self.ng, self.hn
+        g = np_ // ng
+        self._qkv_w = None                 # the re-ordered inference copies go stale once the parameters train
+        x = hidden_states.reshape(s, h)
+        a = self.self_attention
+        hcur = ops.rmsnorm_autograd(x, a.linear_qkv.layer_norm_weight, self.eps)
+        qkv = ops.linear_autograd(hcur, a.linear_qkv.weight, a.linear_qkv.bias).view(s, ng, g + 2, hn)
+        q = qkv[:, :, :g].reshape(s, np_, hn)
+        k = qkv[:, :, g].contiguous()
+        v = qkv[:, :, g + 1].contiguous()
+        if rotary_pos_emb is not None:
+            cos, sin = self._rope(rotary_pos_emb)
+            q = ops.rope_autograd(q, cos, sin)
+            k = ops.rope_autograd(k, cos, sin)
+        att = ops.attention(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), causal=True)       # [1, s, np, hn]
+        o = ops.linear_autograd(att.reshape(s, np_ * hn), a.linear_proj.weight)
+        hcur, x = ops.rmsnorm_autograd(o, self.mlp.linear_fc1.layer_norm_weight, self.eps, residual=x)
+        gate_up = ops.linear_autograd(hcur, self.mlp.linear_fc1.weight)                         # cat(gate, up)
+        d = ops.linear_autograd(ops.swiglu_autograd(gate_up), self.mlp.linear_fc2.weight)
+        return (x + d).view(s, b, h)
 
 
 def get_b200_layer_spec():

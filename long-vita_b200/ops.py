@@ -211,6 +211,68 @@ def attention(q, k, v, *, causal: bool, scale: Optional[float] = None):
     return _AttentionFn.apply(q, k, v, causal, scale)
 
 
+def _sm_count(device) -> int:
+    return torch.cuda.get_device_properties(device).multi_processor_count if torch.cuda.is_available() else 148
+
+
+def attention_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, length: int, *,
+                     scale: Optional[float] = None, n_splits: Optional[int] = None, return_lse: bool = False):
+    """One new token against a K/V cache (the reference has no such path - it re-prefills
+    every generated token, long_vita_megatron/inference/text_generation/generation.py:127-135).
+
+    q [hq, d]; k_cache / v_cache [>= length, hkv, d] (post-RoPE rows of the previous tokens, the new token's
+    row already appended); returns out [hq, d] (and lse [hq] fp32, natural log - what a context-parallel
+    combine across cache shards needs).
+
+    HBM-bound (every K/V row is read once), so the job is to put all SMs on the cache: the G = hq / hkv query
+    heads of a kv group become G query ROWS of one head (they share K/V), and the key range is cut into
+    `n_splits` chunks that run as the batch dimension of the ordinary fused kernel (`lv_attn_fwd`,
+    non-causal, with LSE); the partial results are merged by their log-sum-exp weights (flash-decoding).
+    A ragged last chunk is a second launch with sk = remainder."""
+    _need_cuda_bf16(q, k_cache, v_cache)
+    hq, d = q.shape
+    hkv = k_cache.shape[1]
+    G = hq // hkv
+    if length <= 0 or length > k_cache.shape[0]:
+        raise ValueError(f"attention_decode: length {length} outside the cache (capacity {k_cache.shape[0]})")
+    if n_splits is None:
+        n_splits = max(1, _sm_count(q.device) // hkv)
+    per = -(-length // n_splits)
+    chunk = max(128, (per + 127) // 128 * 128)                             # keys per split, whole 128-key tiles
+    n_full, rem = divmod(length, chunk)
+    qp = q.view(hkv, G, d).transpose(0, 1)                                 # [G rows, hkv heads, d]
+    outs, lses = [], []
+    if n_full:
+        qb = qp.unsqueeze(0).expand(n_full, G, hkv, d).contiguous()
+        kb = k_cache[: n_full * chunk].view(n_full, chunk, hkv, d)
+        vb = v_cache[: n_full * chunk].view(n_full, chunk, hkv, d)
+        o, l = attention_fwd(qb, kb, vb, causal=False, scale=scale, return_lse=True)   # [n, G, hkv, d], [n, hkv, G]
+        outs.append(o)
+        lses.append(l)
+    if rem:
+        o, l = attention_fwd(qp.unsqueeze(0).contiguous(), k_cache[n_full * chunk : length].unsqueeze(0),
+                             v_cache[n_full * chunk : length].unsqueeze(0), causal=False, scale=scale, return_lse=True)
+        outs.append(o)
+        lses.append(l)
+    o = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)              # [n, G, hkv, d]
+    l = lses[0] if len(lses) == 1 else torch.cat(lses, dim=0)              # [n, hkv, G]
+    return decode_merge(o, l, return_lse=return_lse)
+
+
+def decode_merge(o_part: torch.Tensor, lse_part: torch.Tensor, return_lse: bool = False):
+    """o_part [n, G, hkv, d] bf16, lse_part [n, hkv, G] fp32 -> out [hq, d] (head h = kvh * G + g) and the
+    merged log-sum-exp [hq]: out = sum_s exp(lse_s - LSE) o_s (lv_attn_decode_merge)."""
+    _need_cuda_bf16(o_part)
+    _need_cuda(lse_part, torch.float32)
+    n, G, hkv, d = o_part.shape
+    o_part, lse_part = o_part.contiguous(), lse_part.contiguous()
+    out = torch.empty((hkv * G, d), dtype=torch.bfloat16, device=o_part.device)
+    lse = torch.empty((hkv * G,), dtype=torch.float32, device=o_part.device) if return_lse else None
+    _lib.check(_lib.lib().lv_attn_decode_merge(o_part.data_ptr(), lse_part.data_ptr(), out.data_ptr(), _ptr(lse), n, G, hkv, d,
+                                               _stream()), "lv_attn_decode_merge")
+    return (out, lse) if return_lse else out
+
+
 # ------------------------------------------------------------------------------------------------
 # token-wise operators
 # ------------------------------------------------------------------------------------------------
@@ -449,6 +511,182 @@ def masked_linear_dgrad(grad_out: torch.Tensor, weight: torch.Tensor, logit_mask
     gi = linear(grad_out.reshape(m, -1), wt)          # [M, c]
     idx = logit_mask.reshape(-1).nonzero().view(-1)
     return row_scatter_zero(gi, idx, s).view(s, 1, -1)
+
+
+def masked_linear_wgrad(grad_out: torch.Tensor, h: torch.Tensor, logit_mask: torch.Tensor):
+    """dW of masked_linear: dY^T . masked_select(h) -> [vocab, c] (layers.py:451-456, 512-520: `grad_output.t()
+    .matmul(total_input)`).  Runs on the same tcgen05 GEMM with the contraction over the M selected rows: both
+    operands are transposed once ([vocab, M] and [c, M]; M is the number of answer tokens) and M is zero-padded
+    to a multiple of 8 (the GEMM's K granularity)."""
+    _need_cuda_bf16(grad_out, h)
+    s, b, c = h.shape
+    m = grad_out.shape[0]
+    vocab = grad_out.shape[-1]
+    if m == 0:
+        return torch.zeros((vocab, c), dtype=torch.bfloat16, device=h.device)
+    idx = logit_mask.reshape(-1).nonzero().view(-1)
+    sel = row_gather(h.reshape(s, c), idx)                              # [M, c]
+    mp = (m + 7) // 8 * 8
+    gt = torch.zeros((vocab, mp), dtype=torch.bfloat16, device=h.device)
+    gt[:, :m] = grad_out.reshape(m, vocab).t()
+    st = torch.zeros((c, mp), dtype=torch.bfloat16, device=h.device)
+    st[:, :m] = sel.t()
+    return linear(gt, st)                                               # [vocab, c]
+
+
+class _MaskedLinearFn(torch.autograd.Function):
+    """LinearWithGradAccumulationAndAsyncCommunication with `logit_mask` (layers.py:371-456) for tp = 1,
+    no sequence parallelism, no gradient-accumulation fusion: forward = gather + GEMM, backward =
+    dX = masked_scatter(zeros, dY W) and (when the weight trains) dW = dY^T sel."""
+
+    @staticmethod
+    def forward(ctx, h, weight, logit_mask):
+        ctx.save_for_backward(h, weight, logit_mask)
+        return masked_linear(h, weight, logit_mask)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        h, weight, logit_mask = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        gh = gw = None
+        if ctx.needs_input_grad[0]:
+            if grad_out.shape[0] == 0:
+                gh = torch.zeros_like(h)
+            else:
+                gh = masked_linear_dgrad(grad_out, weight, logit_mask)
+        if ctx.needs_input_grad[1]:
+            gw = masked_linear_wgrad(grad_out, h, logit_mask)
+        return gh, gw, None
+
+
+def masked_linear_autograd(h: torch.Tensor, weight: torch.Tensor, logit_mask: torch.Tensor):
+    """Differentiable logit-masked LM head."""
+    return _MaskedLinearFn.apply(h, weight, logit_mask)
+
+
+# ------------------------------------------------------------------------------------------------
+# differentiable building blocks of the decoder layer (training through the `--spec` layer, SURVEY.md 8f-1)
+# ------------------------------------------------------------------------------------------------
+def rmsnorm_bwd(x: torch.Tensor, weight: torch.Tensor, dy: torch.Tensor, eps: float = 1e-6,
+                add_in: Optional[torch.Tensor] = None):
+    """Gradients of rmsnorm(x, weight): returns (dx [+ add_in], dweight).  `x` is the tensor that was normalised."""
+    _need_cuda_bf16(x, weight, dy, add_in)
+    cols = x.shape[-1]
+    x2, dy2 = x.reshape(-1, cols).contiguous(), dy.reshape(-1, cols).contiguous()
+    a2 = None if add_in is None else add_in.reshape(-1, cols).contiguous()
+    rows = x2.shape[0]
+    parts = int(_lib.lib().lv_rmsnorm_bwd_partials(rows, cols))
+    dw_part = torch.empty((parts, cols), dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x2)
+    _lib.check(_lib.lib().lv_rmsnorm_bwd(x2.data_ptr(), weight.data_ptr(), dy2.data_ptr(), _ptr(a2), dx.data_ptr(),
+                                         dw_part.data_ptr(), rows, cols, float(eps), _stream()), "lv_rmsnorm_bwd")
+    return dx.view(x.shape), dw_part.sum(dim=0).to(torch.bfloat16)
+
+
+def swiglu_bwd(gate_up: torch.Tensor, dh: torch.Tensor):
+    _need_cuda_bf16(gate_up, dh)
+    inter = gate_up.shape[-1] // 2
+    g2, d2 = gate_up.reshape(-1, 2 * inter).contiguous(), dh.reshape(-1, inter).contiguous()
+    out = torch.empty_like(g2)
+    _lib.check(_lib.lib().lv_swiglu_bwd(g2.data_ptr(), d2.data_ptr(), out.data_ptr(), g2.shape[0], inter, _stream()),
+               "lv_swiglu_bwd")
+    return out.view(gate_up.shape)
+
+
+class _RMSNormFn(torch.autograd.Function):
+    """y = rmsnorm(x [+ residual]); with a residual also returns the sum (the new residual stream)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, eps):
+        if residual is None:
+            y, s = rmsnorm(x, weight, eps), x
+        else:
+            y, s = rmsnorm(x, weight, eps, residual=residual)
+        ctx.save_for_backward(s, weight)
+        ctx.eps, ctx.has_res = eps, residual is not None
+        return (y, s) if residual is not None else y
+
+    @staticmethod
+    def backward(ctx, dy, ds=None):
+        s, weight = ctx.saved_tensors
+        dx, dw = rmsnorm_bwd(s, weight, dy.contiguous(), ctx.eps, add_in=ds if ctx.has_res else None)
+        return dx, (dx if ctx.has_res else None), dw, None
+
+
+def rmsnorm_autograd(x, weight, eps: float = 1e-6, residual=None):
+    return _RMSNormFn.apply(x, residual, weight, eps)
+
+
+class _SwiGLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate_up):
+        ctx.save_for_backward(gate_up)
+        return swiglu(gate_up)
+
+    @staticmethod
+    def backward(ctx, dh):
+        (gate_up,) = ctx.saved_tensors
+        return swiglu_bwd(gate_up, dh.contiguous())
+
+
+def swiglu_autograd(gate_up):
+    return _SwiGLUFn.apply(gate_up)
+
+
+class _RopeFn(torch.autograd.Function):
+    """rotate-half RoPE is linear in x: the gradient is the same rotation with -sin."""
+
+    @staticmethod
+    def forward(ctx, x, cos, sin):
+        ctx.save_for_backward(cos, sin)
+        return rope(x, cos, sin)
+
+    @staticmethod
+    def backward(ctx, dy):
+        cos, sin = ctx.saved_tensors
+        dy = dy if dy.stride(2) == 1 else dy.contiguous()
+        return rope(dy, cos, -sin), None, None
+
+
+def rope_autograd(x, cos, sin):
+    return _RopeFn.apply(x, cos, sin)
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM; dX = dY W and dW = dY^T X reuse the same kernel on operands transposed once
+    per call (the [N, K] operand of each product must be K-contiguous); the token count is zero-padded to a multiple
+    of 8 for the weight gradient (the GEMM's K granularity)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        n_out, k_in = weight.shape
+        dy2 = dy.reshape(-1, n_out).contiguous()
+        x2 = x.reshape(-1, k_in)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = linear(dy2, weight.t().contiguous()).view(x.shape)          # [T, K] = dY [T, N] . (W^T)[K, N]^T
+        if ctx.needs_input_grad[1]:
+            t = dy2.shape[0]
+            tp = (t + 7) // 8 * 8
+            dyt = torch.zeros((n_out, tp), dtype=torch.bfloat16, device=dy.device)
+            dyt[:, :t] = dy2.t()
+            xt = torch.zeros((k_in, tp), dtype=torch.bfloat16, device=dy.device)
+            xt[:, :t] = x2.t()
+            dw = linear(dyt, xt)                                             # [N, K] = dY^T [N, T] . (X^T)[K, T]^T
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.float().sum(dim=0).to(torch.bfloat16)
+        return dx, dw, db
+
+
+def linear_autograd(x, weight, bias=None):
+    return _LinearFn.apply(x, weight, bias)
 
 
 def patch_embed(images: torch.Tensor, w_pad: torch.Tensor, bias: Optional[torch.Tensor], cls: torch.Tensor,

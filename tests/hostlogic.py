@@ -41,6 +41,46 @@ def _attention_fwd(q, k, v, *, causal, scale=None, layout="bshd", return_lse=Fal
     return (o, lse) if return_lse else o
 
 
+def _seg_pos(sq, q_seg_len, q_seg_pos):
+    if q_seg_len is not None and q_seg_pos is not None:
+        return torch.cat([torch.arange(q_seg_len) + q_seg_pos[i] for i in range(sq // q_seg_len)])
+    if q_seg_pos is not None:
+        return torch.arange(sq) + q_seg_pos[0]
+    return None
+
+
+def _attention_bwd(d_out, q, k, v, out, lse, *, causal, scale=None, q_seg_len=None, q_seg_pos=None, kv_pos0=0):
+    with torch.enable_grad():      # the oracle differentiates by autograd; this runs inside an autograd backward
+        dq, dk, dv = O.attention_grads(q, k, v, d_out, causal=causal, scale=scale,
+                                       q_pos=_seg_pos(q.shape[1], q_seg_len, q_seg_pos), kv_pos=torch.arange(k.shape[1]) + kv_pos0)
+    return _bf(dq), _bf(dk), _bf(dv)
+
+
+def _decode_merge(o_part, lse_part, return_lse=False):
+    n, G, hkv, d = o_part.shape
+    lse = torch.logsumexp(lse_part, dim=0)                                            # [hkv, G]
+    w = torch.exp(lse_part - lse.unsqueeze(0)).permute(0, 2, 1).unsqueeze(-1)          # [n, G, hkv, 1]
+    out = _bf((o_part.float() * w).sum(dim=0)).transpose(0, 1).reshape(hkv * G, d)
+    return (out, lse.reshape(hkv * G)) if return_lse else out
+
+
+def _rmsnorm_bwd(x, weight, dy, eps=1e-6, add_in=None):
+    with torch.enable_grad():
+        xf = x.detach().float().requires_grad_(True)
+        wf = weight.detach().float().requires_grad_(True)
+        y = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps) * wf
+        y.backward(dy.float())
+    dx = xf.grad if add_in is None else xf.grad + add_in.float()
+    return _bf(dx), _bf(wf.grad)
+
+
+def _swiglu_bwd(gate_up, dh):
+    with torch.enable_grad():
+        gu = gate_up.detach().float().requires_grad_(True)
+        O.swiglu(gu).backward(dh.float())
+    return _bf(gu.grad)
+
+
 def _rmsnorm(x, weight, eps=1e-6, residual=None):
     if residual is None:
         return O.rmsnorm(x, weight, eps)
@@ -101,7 +141,11 @@ def _row_scatter_zero(x, idx, n_rows_out):
 
 SUBSTITUTES = {
     "attention_fwd": _attention_fwd,
+    "attention_bwd": _attention_bwd,
+    "decode_merge": _decode_merge,
     "rmsnorm": _rmsnorm,
+    "rmsnorm_bwd": _rmsnorm_bwd,
+    "swiglu_bwd": _swiglu_bwd,
     "layernorm": lambda x, w, b, eps=1e-6: O.layernorm(x, w, b, eps),
     "rope_table": _rope_table,
     "rope": _rope,

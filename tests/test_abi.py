@@ -146,3 +146,21 @@ def test_product_package_never_imports_the_oracle():
                 if any(n == "oracle" or n.startswith("oracle.") or n == "tests" or n.startswith("tests.") for n in names):
                     offenders.append(os.path.join(dirpath, f))
     assert not offenders, offenders
+
+
+def test_context_parallel_argument_errors(lib_built):
+    from long_vita_b200 import _lib
+    from long_vita_b200._lib import CpParams
+
+    h = _lib.lib()
+    a = _attn_params()
+    c = CpParams()
+    c.rank, c.cp, c.seq_total = 0, 9, 4096
+    assert h.lv_attn_cp_fwd(ctypes.byref(a), ctypes.byref(c), None) == -1 and b"bad rank" in h.lv_last_error()
+    c.cp = 2
+    c.seq_total = 4098
+    assert h.lv_attn_cp_fwd(ctypes.byref(a), ctypes.byref(c), None) == -1 and b"not divisible by 2*cp" in h.lv_last_error()
+    c.seq_total = 4 * 100
+    assert h.lv_attn_cp_fwd(ctypes.byref(a), ctypes.byref(c), None) == -1 and b"multiple of 128" in h.lv_last_error()
+    c.seq_total = 4 * 128
+    assert h.lv_attn_cp_fwd(ctypes.byref(a), ctypes.byref(c), None) == -1 and b"staging buffers" in h.lv_last_error()

@@ -144,3 +144,22 @@ def test_attention_vs_flash_attn_comparator(L):
     theirs = fa.flash_attn_func(q.cuda(), k.cuda(), v.cuda(), causal=True)
     e_ours, e_theirs = excess_error(ours, ref)[0], excess_error(theirs, ref)[0]
     assert e_ours < 1.25 * e_theirs, (e_ours, e_theirs)
+
+
+@pytest.mark.parametrize("length,n_splits", [(1, None), (100, None), (5000, None), (5000, 1), (4096, 4), (33000, None)])
+def test_attention_decode(lib_built, length, n_splits):
+    """One query token against a K/V cache (LLM geometry 40:8 x 128): GQA heads packed as query rows, key range
+    split over the batch dimension of lv_attn_fwd, log-sum-exp merge."""
+    from long_vita_b200 import ops
+
+    g = seeded(900 + length)
+    hq, hkv, d = 40, 8, 128
+    cap = (length + 255) // 128 * 128
+    q = randn_bf16((hq, d), g)
+    kc, vc = randn_bf16((cap, hkv, d), g), randn_bf16((cap, hkv, d), g)
+    out, lse = ops.attention_decode(q.cuda(), kc.cuda(), vc.cuda(), length, n_splits=n_splits, return_lse=True)
+    ref, ref_lse = O.attention(q[None, None], kc[None, :length], vc[None, :length], causal=False)
+    assert out.shape == (hq, d)
+    assert float((lse.cpu() - ref_lse[0, :, 0]).abs().max()) < 1e-4
+    # one bf16 rounding of the partial outputs + one of the merged result
+    assert rel_fro(out, ref[0, 0]) < 6e-3, rel_fro(out, ref[0, 0])

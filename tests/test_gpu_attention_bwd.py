@@ -68,3 +68,28 @@ def test_backward_is_deterministic(lib_built):
     (a1, b1, c1), _, _ = run(640, 640, 10, 2, 128, True, seed=3)
     (a2, b2, c2), _, _ = run(640, 640, 10, 2, 128, True, seed=3)
     assert torch.equal(a1, a2) and torch.equal(b1, b2) and torch.equal(c1, c2)
+
+
+@pytest.mark.parametrize("cp,rank", [(2, 0), (2, 1), (4, 1)])
+def test_backward_of_zigzag_query_segments(lib_built, cp, rank):
+    """What one context-parallel rank runs in backward (cp.CPBackwardMixin): its two query chunks at their
+    global positions against the whole K/V.  dQ is final; dK/dV are partial sums and must be exactly zero on
+    kv rows none of the local queries can see."""
+    from long_vita_b200 import ops
+
+    c, hq, hkv, d = 256, 10, 2, 128
+    S = 2 * cp * c
+    g = seeded(40 + rank)
+    q, k, v = randn_bf16((1, S, hq, d), g), randn_bf16((1, S, hkv, d), g), randn_bf16((1, S, hkv, d), g)
+    do = randn_bf16((1, S, hq, d), g)
+    own = torch.cat([torch.arange(rank * c, (rank + 1) * c), torch.arange((2 * cp - 1 - rank) * c, (2 * cp - rank) * c)])
+    ql, dol = q[:, own].contiguous(), do[:, own].contiguous()
+    rq, rk, rv = O.attention_grads(ql, k, v, dol, causal=True, q_pos=own, kv_pos=torch.arange(S))
+    seg = dict(q_seg_len=c, q_seg_pos=(rank * c, (2 * cp - 1 - rank) * c))
+    out, lse = ops.attention_fwd(ql.cuda(), k.cuda(), v.cuda(), causal=True, return_lse=True, **seg)
+    dq, dk, dv = ops.attention_bwd(dol.cuda(), ql.cuda(), k.cuda(), v.cuda(), out, lse, causal=True, **seg)
+    for name, a, r in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+        assert torch.isfinite(a).all(), name
+        assert excess(a, r) < 3e-3, (name, excess(a, r))
+    last_visible = (2 * cp - rank) * c
+    assert not dk[:, last_visible:].any() and not dv[:, last_visible:].any()

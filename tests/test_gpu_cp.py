@@ -60,6 +60,26 @@ def _worker(rank, world, port):
             assert math.sqrt(max(e * e - e_floor * e_floor, 0.0)) < 2e-3, (rank, epoch, e, e_floor)
         dist.barrier()
 
+        # ---- the 14B K/V geometry (8 kv heads x 128 = 4 KB K|V rows): the copier's one-row-per-pass fast path ----
+        hq2, hkv2 = 40, 8
+        S2 = 2 * world * 128
+        ctx2 = CP.CPContext(dist.group.WORLD, S2, hq2, hkv2, d, dev)
+        own2 = CP.zigzag_index(S2, world, rank)
+        for epoch in range(2):
+            g = torch.Generator().manual_seed(300 + epoch)
+            qkv = torch.randn(S2, (hq2 + 2 * hkv2) * d, generator=g).to(torch.bfloat16)
+            ctx2.qkv_buffer().copy_(qkv[own2].to(dev))
+            out = ctx2.attention()
+            q = qkv[:, : hq2 * d].view(1, S2, hq2, d)
+            k = qkv[:, hq2 * d : (hq2 + hkv2) * d].view(1, S2, hkv2, d)
+            v = qkv[:, (hq2 + hkv2) * d :].view(1, S2, hkv2, d)
+            ref, _ = O.attention(q, k, v, causal=True)
+            ref_l = ref[0, own2].reshape(own2.numel(), hq2 * d)
+            e = _rel(out, ref_l)
+            e_floor = _rel(ref_l.to(torch.bfloat16), ref_l)
+            assert math.sqrt(max(e * e - e_floor * e_floor, 0.0)) < 2e-3, (rank, epoch, e, e_floor)
+        dist.barrier()
+
         # ---- whole sharded prefill vs the single-device forward ----
         cfg = LongVITAConfig.tiny(layers=3, vit_layers=1)
         w = synthetic_state_dict(cfg, seed=11, dtype=torch.bfloat16, perturb=True)
@@ -81,3 +101,81 @@ def test_context_parallel_matches_single_device(lib_built, world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     mp.spawn(_worker, args=(world, _free_port()), nprocs=world, join=True)
+
+
+def _bwd_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from long_vita_b200 import cp as CP
+        from oracle import ops as O
+
+        hq, hkv, d = 10, 2, 128
+        S = 2 * world * 256
+        ctx = CP.CPContext(dist.group.WORLD, S, hq, hkv, d, dev, fused_qkv=False)
+        own = CP.zigzag_index(S, world, rank)
+        for step in range(2):                                   # two steps: both buffer parities, epochs continue
+            g = torch.Generator().manual_seed(500 + step)       # same tensors on every rank
+            q = torch.randn(S, hq, d, generator=g).to(torch.bfloat16)
+            k = torch.randn(S, hkv, d, generator=g).to(torch.bfloat16)
+            v = torch.randn(S, hkv, d, generator=g).to(torch.bfloat16)
+            d_out = torch.randn(S, hq * d, generator=g).to(torch.bfloat16)
+            ql, kl, vl = (t[own].to(dev).requires_grad_(True) for t in (q, k, v))
+            out = CP.cp_attention(ql, kl, vl, ctx)
+            out.backward(d_out[own].to(dev))
+            dq, dk, dv = O.attention_grads(q[None], k[None], v[None], d_out.view(1, S, hq, d), causal=True)
+            for name, got, ref in (("dq", ql.grad, dq[0][own]), ("dk", kl.grad, dk[0][own]), ("dv", vl.grad, dv[0][own])):
+                e = _rel(got, ref)
+                # single-GPU backward tolerance (tests/test_gpu_attention_bwd.py) plus one bf16 rounding of the
+                # partial dK/dV before the reduce-scatter
+                assert e < 8e-3, (rank, step, name, e)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_context_parallel_backward_matches_single_device(lib_built, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    mp.spawn(_bwd_worker, args=(world, _free_port()), nprocs=world, join=True)
+
+
+def _decode_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from long_vita_b200 import cp as CP
+        from long_vita_b200.config import LongVITAConfig
+        from long_vita_b200.hf.modeling import LongVITAForCausalLM
+        from long_vita_b200.synthetic import build_prompt, synthetic_frames
+        from long_vita_b200.weights import synthetic_state_dict
+
+        cfg = LongVITAConfig.tiny(layers=3, vit_layers=1)
+        w = synthetic_state_dict(cfg, seed=11, dtype=torch.bfloat16, perturb=True)
+        model = LongVITAForCausalLM(cfg, {k_: t.to(dev) for k_, t in w.items()})
+        ids, idx = build_prompt(cfg, 3, n_text=30, pad_multiple=2 * world * 128, seed=3)
+        images = synthetic_frames(cfg, 3, seed=3)
+        S = ids.shape[1]
+        new = torch.randint(0, cfg.vocab_size, (4,), generator=torch.Generator().manual_seed(6))
+        full = model(input_ids=torch.cat([ids, new.view(1, 4)], dim=1).to(dev), images=images.to(dev),
+                     image_indices=idx.to(dev)).logits
+        runner = CP.ContextParallelRunner(model, dist.group.WORLD)
+        first = runner.forward(ids.to(dev), images.to(dev), idx.to(dev), use_cache=True, max_new_tokens=16)
+        assert _rel(first[0, 0], full[0, S - 1]) < 1.5e-2
+        for i in range(4):
+            lg = runner.decode(new[i].to(dev))
+            assert _rel(lg[0, 0], full[0, S + i]) < 2e-2, (rank, i, _rel(lg[0, 0], full[0, S + i]))
+            assert int(lg[0, 0].float().argmax()) == int(full[0, S + i].float().argmax())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_context_parallel_sharded_cache_decode(lib_built, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    mp.spawn(_decode_worker, args=(world, _free_port()), nprocs=world, join=True)

@@ -159,3 +159,52 @@ def test_row_gather_scatter_bit_exact(L):
     assert torch.equal(back.cpu(), ref)
     empty = L.row_gather(x.cuda(), idx[:0].cuda())
     assert empty.shape == (0, 5120)
+
+
+def test_rmsnorm_backward(L):
+    g = seeded(31)
+    for rows, cols in ((300, 5120), (77, 640), (1000, 1024)):
+        x, dy = randn_bf16((rows, cols), g, 2.0), randn_bf16((rows, cols), g)
+        w = (1 + 0.1 * torch.randn(cols, generator=g)).to(torch.bfloat16)
+        add = randn_bf16((rows, cols), g)
+        xf, wf = x.float().requires_grad_(True), w.float().requires_grad_(True)
+        (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * wf).backward(dy.float())
+        dx, dw = L.rmsnorm_bwd(x.cuda(), w.cuda(), dy.cuda(), 1e-6)
+        assert rel_fro(dx, xf.grad) < 4e-3 and rel_fro(dw, wf.grad) < 4e-3, (rows, cols, rel_fro(dx, xf.grad), rel_fro(dw, wf.grad))
+        dx2, _ = L.rmsnorm_bwd(x.cuda(), w.cuda(), dy.cuda(), 1e-6, add_in=add.cuda())
+        assert rel_fro(dx2, xf.grad + add.float()) < 4e-3
+    # through the autograd function, fused residual form
+    x, r = randn_bf16((64, 640), g).cuda().requires_grad_(True), randn_bf16((64, 640), g).cuda().requires_grad_(True)
+    w = torch.ones(640, dtype=torch.bfloat16, device="cuda", requires_grad=True)
+    y, s = L.rmsnorm_autograd(x, w, 1e-6, residual=r)
+    (y.float().sum() + 2 * s.float().sum()).backward()
+    assert torch.equal(x.grad, r.grad) and x.grad.shape == x.shape and w.grad.shape == w.shape
+
+
+def test_swiglu_backward(L):
+    g = seeded(32)
+    gu, dh = randn_bf16((257, 2 * 1024), g, 2.0), randn_bf16((257, 1024), g)
+    guf = gu.float().requires_grad_(True)
+    O.swiglu(guf).backward(dh.float())
+    d = L.swiglu_bwd(gu.cuda(), dh.cuda())
+    assert rel_fro(d, guf.grad) < 4e-3, rel_fro(d, guf.grad)
+
+
+def test_linear_and_rope_autograd(L):
+    g = seeded(33)
+    x, w, b = randn_bf16((203, 640), g), randn_bf16((384, 640), g, 0.05), randn_bf16((384,), g)
+    dy = randn_bf16((203, 384), g)
+    xg, wg, bg = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    L.linear_autograd(xg, wg, bg).backward(dy.cuda())
+    xf, wf, bf_ = (t.float().requires_grad_(True) for t in (x, w, b))
+    (xf @ wf.t() + bf_).backward(dy.float())
+    assert rel_fro(xg.grad, xf.grad) < 3e-3 and rel_fro(wg.grad, wf.grad) < 3e-3 and rel_fro(bg.grad, bf_.grad) < 3e-3
+    t = randn_bf16((128, 5, 128), g)
+    inv = O.rope_inv_freq(128, 1e6)
+    cos, sin = O.rope_tables(torch.arange(128), inv, torch.bfloat16)
+    tg = t.cuda().requires_grad_(True)
+    dyr = randn_bf16((128, 5, 128), g)
+    L.rope_autograd(tg, cos.cuda(), sin.cuda()).backward(dyr.cuda())
+    tf = t.float().requires_grad_(True)
+    O.rope_apply(tf, cos.float(), sin.float()).backward(dyr.float())
+    assert rel_fro(tg.grad, tf.grad) < 4e-3

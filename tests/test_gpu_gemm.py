@@ -109,3 +109,23 @@ def test_gemm_fused_swiglu_epilogue_is_bit_exact_with_unfused_pair(L):
     assert torch.equal(fused, unfused)
     ref = O.swiglu(ref_linear(x, torch.cat([gate, up])))
     assert rel_fro(fused, ref) < 1.5e-3
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 4])
+@pytest.mark.parametrize("act", [None, "gelu", "swiglu"])
+def test_small_m_weight_stream_path(L, M, act):
+    """M <= 4 (decode) runs the HBM-bound GEMV kernel instead of a 128-row tensor-core tile; same epilogue
+    arithmetic.  N = 1000 / 1008 and K = 328 exercise the odd-column tail and a K that is not a multiple of
+    the 256-element warp stride."""
+    g = seeded(50 + M)
+    for N, K in ((5120, 5120), (1008 if act == "swiglu" else 1000, 328)):
+        x, w = randn_bf16((M, K), g), randn_bf16((N, K), g, 0.05)
+        b = None if act == "swiglu" else randn_bf16((N,), g)
+        y = L.linear(x.cuda(), w.cuda(), None if b is None else b.cuda(), act)
+        if act == "swiglu":
+            full = (x.float() @ w.float().t()).to(torch.bfloat16)
+            ref = (F.silu(full[:, 0::2].float()).to(torch.bfloat16).float() * full[:, 1::2].float()).to(torch.bfloat16)
+            assert y.shape == (M, N // 2)
+        else:
+            ref = ref_linear(x, w, b, act)
+        assert rel_fro(y, ref) < 2e-3, (N, K, rel_fro(y, ref))

@@ -100,7 +100,7 @@ def test_signature_guards(setup):
     model = M.LongVITAForCausalLM(cfg, wg)
     ids = torch.zeros(1, 8, dtype=torch.long).cuda()
     with pytest.raises(NotImplementedError):
-        model(input_ids=ids, use_cache=True)
+        model(input_ids=ids, output_attentions=True)
     with pytest.raises(ValueError):
         model(input_ids=None)
 
@@ -159,3 +159,27 @@ def test_whole_forward_matches_the_references_own_forward(lib_built):
     rows = gold["rows"]
     for li in range(cfg.num_hidden_layers + 1):
         assert rel_fro(out.hidden_states[li][0].cpu()[rows], gold["hidden_rows"][li]) < 1.5e-2, li
+
+
+def test_kv_cache_decode_matches_full_forward(setup):
+    """8f-2 on the kernels: prefill with use_cache, single-token decode steps (flash-decoding composition over
+    lv_attn_fwd) and a 3-token chunk against the full forward over the extended sequence."""
+    cfg, w, wg, M = setup
+    ids, images, idx = make_inputs(cfg, s=700)
+    extra = torch.randint(0, cfg.vocab_size, (1, 6), generator=torch.Generator().manual_seed(8))
+    model = M.LongVITAForCausalLM(cfg, wg)
+    full = model(input_ids=torch.cat([ids, extra], dim=1).cuda(), images=images.cuda(), image_indices=idx.cuda()).logits
+    out = model(input_ids=ids.cuda(), images=images.cuda(), image_indices=idx.cuda(), use_cache=True,
+                num_logits_to_keep=1, max_cache_len=1024)
+    cache = out.past_key_values
+    assert len(cache) == 700
+    assert rel_fro(out.logits[0, -1], full[0, 699]) < 1e-2
+    for i in range(3):
+        out = model(input_ids=extra[:, i : i + 1].cuda(), past_key_values=cache, use_cache=True)
+        assert len(cache) == 701 + i
+        assert rel_fro(out.logits[0, 0], full[0, 700 + i]) < 1.5e-2, (i, rel_fro(out.logits[0, 0], full[0, 700 + i]))
+        assert int(out.logits[0, 0].float().argmax()) == int(full[0, 700 + i].float().argmax())
+    out = model(input_ids=extra[:, 3:].cuda(), past_key_values=cache, use_cache=True)
+    assert len(cache) == 706 and rel_fro(out.logits[0], full[0, 703:]) < 1.5e-2
+    gen = model.generate_greedy(ids.cuda(), images.cuda(), idx.cuda(), max_new_tokens=4)
+    assert gen.shape == (1, 4)

@@ -146,3 +146,67 @@ def test_whole_layer_spec_module_matches_oracle_decoder_layer(lib_built):
     cos, sin = O.rope_tables(torch.arange(s), inv, torch.bfloat16)
     ref = OM.decoder_layer(cfg, OM.cast_weights(w, torch.float32), 0, x[:, 0].float(), cos.float(), sin.float())
     assert rel_fro(out[:, 0], ref) < 4e-3, rel_fro(out[:, 0], ref)
+
+
+def test_masked_lm_head_autograd(lib_built):
+    """a12 backward on the kernels: dX scatter and dW = dY^T sel through the transposed-operand GEMM (K = M
+    padded to 8)."""
+    from long_vita_b200 import ops
+
+    g = seeded(12)
+    s, c, vocab = 300, 640, 2048
+    h = randn_bf16((s, 1, c), g)
+    w = randn_bf16((vocab, c), g, scale=0.05)
+    mask = torch.zeros(1, s, dtype=torch.bool)
+    mask[0, [5, 6, 77, 150, 299]] = True
+    dy = randn_bf16((5, 1, vocab), g)
+    hg, wg = h.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    out = ops.masked_linear_autograd(hg, wg, mask.cuda())
+    out.backward(dy.cuda())
+    ref_out = O.masked_linear_fwd(h.float(), w.float(), mask)
+    gx, gw = O.masked_linear_bwd(dy.float(), h.float(), w.float(), mask)
+    assert rel_fro(out, ref_out) < 4e-3
+    assert rel_fro(hg.grad, gx) < 4e-3 and rel_fro(wg.grad, gw) < 4e-3
+
+
+def test_spec_layer_training_step_matches_oracle_autograd(lib_built):
+    """B2 training path on the kernels: forward + backward of the `--spec` layer (RMSNorm / SwiGLU / RoPE backward
+    kernels, lv_attn_bwd, GEMM dX / dW) against fp32 autograd through the oracle decoder layer."""
+    from types import SimpleNamespace
+
+    from long_vita_b200.config import LongVITAConfig
+    from long_vita_b200.megatron import checkpoint as ck
+    from long_vita_b200.megatron.transformer_layer import B200TransformerLayer
+    from long_vita_b200.weights import llm_layer_weights
+    from oracle import model as OM
+
+    cfg = LongVITAConfig.tiny(layers=1)
+    hf = llm_layer_weights(cfg, 0, seed=9, dtype=torch.bfloat16, perturb=True)
+    mc = ck.hf_to_mcore(hf, cfg)
+    mcfg = SimpleNamespace(hidden_size=cfg.hidden_size, num_attention_heads=cfg.num_attention_heads,
+                           num_query_groups=cfg.num_key_value_heads, kv_channels=cfg.head_dim,
+                           ffn_hidden_size=cfg.intermediate_size, layernorm_epsilon=cfg.rms_norm_eps,
+                           hidden_dropout=0.0, attention_dropout=0.0, params_dtype=torch.bfloat16)
+    layer = B200TransformerLayer(mcfg, layer_number=1)
+    layer.load_state_dict({k[len("decoder.layers.0."):]: v.cuda() for k, v in mc.items()}, strict=True)
+    for prm in layer.parameters():
+        prm.requires_grad_(True)
+    s = 384
+    g_ = seeded(10)
+    x = randn_bf16((s, 1, cfg.hidden_size), g_).cuda().requires_grad_(True)
+    dout = randn_bf16((s, 1, cfg.hidden_size), g_, 0.1)
+    inv = O.rope_inv_freq(cfg.head_dim, cfg.rope_theta)
+    freqs = torch.outer(torch.arange(s).float(), inv)
+    emb = torch.cat((freqs, freqs), dim=-1)[:, None, None, :]
+    out, _ = layer(hidden_states=x, attention_mask=None, rotary_pos_emb=emb.cuda())
+    out.backward(dout.cuda())
+    w32 = {k: v.float().requires_grad_(True) for k, v in hf.items()}
+    xr = x.detach().float().cpu()[:, 0].requires_grad_(True)
+    cos, sin = O.rope_tables(torch.arange(s), inv, torch.float32)
+    ref = OM.decoder_layer(cfg, w32, 0, xr, cos, sin)
+    ref.backward(dout.float()[:, 0])
+    assert rel_fro(out[:, 0], ref.detach()) < 8e-3
+    assert rel_fro(x.grad[:, 0], xr.grad) < 2e-2
+    ref_mc = ck.hf_to_mcore({k: v.grad for k, v in w32.items()}, cfg)
+    for name, prm in layer.named_parameters():
+        assert rel_fro(prm.grad, ref_mc["decoder.layers.0." + name]) < 3e-2, name

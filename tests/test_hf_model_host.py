@@ -71,7 +71,7 @@ def test_guards_raise_before_any_kernel_call(setup):
         model(input_ids=None)
     with pytest.raises(ValueError):
         model(input_ids=ids, inputs_embeds=torch.zeros(1, 8, cfg.hidden_size))
-    for kw in ({"use_cache": True}, {"output_attentions": True}, {"past_key_values": [1]},
+    for kw in ({"output_attentions": True}, {"past_key_values": [1]},
                {"attention_mask": torch.tensor([[1, 1, 1, 1, 1, 1, 0, 0]])}):
         with pytest.raises(NotImplementedError):
             model(input_ids=ids, **kw)
@@ -109,3 +109,97 @@ def test_product_composition_against_the_references_own_forward():
     with oracle_ops():
         loss = model(input_ids=ids, images=images.to(torch.bfloat16), image_indices=idx, labels=golden_labels(ids)).loss
     assert abs(float(loss) - float(gold["loss"])) < 2e-2 * float(gold["loss"]), (float(loss), float(gold["loss"]))
+
+
+
+
+def test_kv_cache_decode_equals_full_forward(setup):
+    """8f-2: prefill with use_cache, then single-token steps and a 3-token chunk through the cache must give
+    the logits of a full forward over the extended sequence (same operators per token; only the attention's
+    split / merge order differs)."""
+    cfg, w, model, w32 = setup
+    ids, images, idx = _inputs(cfg, s=290)
+    extra = torch.randint(0, cfg.vocab_size, (1, 5), generator=torch.Generator().manual_seed(77))
+    with oracle_ops():
+        full = model(input_ids=torch.cat([ids, extra], dim=1), images=images, image_indices=idx).logits   # [1, 295, V]
+        out = model(input_ids=ids, images=images, image_indices=idx, use_cache=True, num_logits_to_keep=1, max_cache_len=400)
+        cache = out.past_key_values
+        assert len(cache) == 290 and cache.get_seq_length() == 290 and cache.capacity == 400
+        assert rel_fro(out.logits[0, -1], full[0, 289]) < 4e-3
+        for i in range(2):                                     # one token at a time -> ops.attention_decode
+            out = model(input_ids=extra[:, i : i + 1], past_key_values=cache, use_cache=True, images=images, image_indices=idx)
+            assert out.past_key_values is cache and len(cache) == 291 + i
+            # the split partial outputs are bf16 (one extra rounding before the merge; with n_splits = 1 the
+            # step is bit-identical to the full forward): 6e-3 on the logits of this 2-layer model
+            assert rel_fro(out.logits[0, 0], full[0, 290 + i]) < 1e-2, i
+        out = model(input_ids=extra[:, 2:], past_key_values=cache, use_cache=True)      # 3 tokens: chunked prefill
+        assert len(cache) == 295 and out.logits.shape == (1, 3, cfg.vocab_size)
+        assert rel_fro(out.logits[0], full[0, 292:]) < 1e-2
+        with pytest.raises(RuntimeError, match="overflow"):
+            model(input_ids=torch.zeros(1, 200, dtype=torch.long), past_key_values=cache, use_cache=True)
+
+
+def test_attention_decode_splits_and_merges(setup):
+    """Flash-decoding composition: GQA heads packed as query rows, key range split into batch entries plus a
+    ragged remainder, log-sum-exp merge - against one plain attention over the same keys."""
+    from oracle import ops as O
+
+    g = torch.Generator().manual_seed(3)
+    hq, hkv, d, L = 10, 2, 32, 700
+    q = torch.randn(hq, d, generator=g).to(torch.bfloat16)
+    kc = torch.randn(1024, hkv, d, generator=g).to(torch.bfloat16)
+    vc = torch.randn(1024, hkv, d, generator=g).to(torch.bfloat16)
+    ref, ref_lse = O.attention(q[None, None], kc[None, :L], vc[None, :L], causal=False)
+    with oracle_ops() as ops:
+        for n_splits in (1, 3, 18):
+            out, lse = ops.attention_decode(q, kc, vc, L, n_splits=n_splits, return_lse=True)
+            assert out.shape == (hq, d) and lse.shape == (hq,)
+            assert rel_fro(out, ref[0, 0]) < 6e-3, n_splits
+            assert torch.allclose(lse, ref_lse[0, :, 0], atol=1e-4), n_splits
+        with pytest.raises(ValueError):
+            ops.attention_decode(q, kc, vc, 2000)
+
+
+def test_generate_greedy_matches_re_prefill(setup):
+    cfg, w, model, _ = setup
+    ids, images, idx = _inputs(cfg, s=290)
+    with oracle_ops():
+        gen = model.generate_greedy(ids, images, idx, max_new_tokens=3)
+        # the reference's loop: feed everything again, take the last row
+        seq = ids
+        want = []
+        for _ in range(3):
+            tok = model(input_ids=seq, images=images, image_indices=idx, num_logits_to_keep=1).logits[0, -1].float().argmax()
+            want.append(int(tok))
+            seq = torch.cat([seq, tok.view(1, 1)], dim=1)
+    assert gen.shape == (1, 3) and gen[0].tolist() == want
+
+
+def test_kv_cache_decode_against_the_references_own_incremental_decoding():
+    """The build's decode path (prefill with use_cache, then single-token steps through ops.attention_decode; kernels
+    replaced by the oracle) against the committed logits of the reference's own DynamicCache decoding
+    (tests/golden/ref_long_vita_decode.pt)."""
+    import os
+    import sys
+
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold_dir)
+    from make_golden import decode_new_tokens, long_vita_inputs
+
+    dec = torch.load(os.path.join(gold_dir, "ref_long_vita_decode.pt"))
+    cfg = LongVITAConfig.tiny(layers=2, vit_layers=1)
+    w = synthetic_state_dict(cfg, seed=dec["seed"], dtype=torch.float32, perturb=True)
+    ids, images, idx = long_vita_inputs(cfg, dec["seed"])
+    new = decode_new_tokens(cfg)
+    model = LongVITAForCausalLM(cfg, {k: v.to(torch.bfloat16) for k, v in w.items()})
+    with oracle_ops():
+        out = model(input_ids=ids, images=images.to(torch.bfloat16), image_indices=idx, use_cache=True, num_logits_to_keep=1,
+                    max_cache_len=ids.shape[1] + 8)
+        assert rel_fro(out.logits[0, -1], dec["prefill_last"]) < 2e-2
+        cache = out.past_key_values
+        for i in range(new.shape[1]):
+            o = model(input_ids=new[:, i : i + 1], past_key_values=cache, use_cache=True, images=images.to(torch.bfloat16),
+                      image_indices=idx)
+            assert rel_fro(o.logits[0, 0], dec["steps"][i]) < 2e-2, (i, rel_fro(o.logits[0, 0], dec["steps"][i]))
+            assert int(o.logits[0, 0].float().argmax()) == int(dec["steps"][i].argmax())
+        assert len(cache) == dec["cache_len"]
