@@ -104,15 +104,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline (oracle port of the reference HF forward), bounded sample + extrapolation
+# CPU baseline (oracle port of the reference HF forward), bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(cfg, total_tokens: int, n_frames: int, threads: int, sample_tokens: int = 2048):
-    """Time the oracle on a bounded sample and extrapolate to one full prefill of `total_tokens`.
+_REF_CACHE = {}    # synthetic fp32 weights / inputs of the CPU sample (generated once, outside the timed parts)
 
-    Sample: ONE of the 48 decoder layers on `sample_tokens` tokens (attention timed separately from
-    the token-wise part), ONE frame through 2 of the 24 ViT layers + the projector, and the LM head
-    on one row.  Extrapolation: token-wise cost scales linearly with S, attention quadratically,
-    ViT linearly with frames and layers.  Returns (tokens_per_sec, seconds_measured, description)."""
+
+def cpu_reference_sample(cfg, total_tokens: int, n_frames: int, threads: int):
+    """Time the oracle port of the reference's HF forward on a bounded sample of ONE prefill of `total_tokens`.
+
+    Sample (everything at the FULL sequence length - nothing is extrapolated in S):
+      * one of the L identical decoder layers on all `total_tokens` tokens: the whole token-wise part (RMSNorm, QKV,
+        RoPE, O-proj, SwiGLU MLP) plus the eager causal attention (full S x S scores, then the mask - what the
+        reference's HF path computes on a CPU, where flash-attn cannot run) of ONE of the hkv identical kv groups
+        (hq / hkv query heads), timed apart inside the same layer call;
+      * one of the F identical frames through the whole ViT tower (all layers) + projector.
+    Scaled only by counts of identical units: t_prefill = L * (t_tokenwise + hkv * t_attn_group) + F * t_frame.
+    Returns (tokens_per_sec, seconds_measured, description)."""
     import torch
 
     from long_vita_b200.weights import global_weights, llm_layer_weights, vit_layer_weights
@@ -120,44 +127,131 @@ def cpu_reference_sample(cfg, total_tokens: int, n_frames: int, threads: int, sa
     from oracle import ops as O
 
     torch.set_num_threads(threads)
-    S = min(sample_tokens, total_tokens)
-    w = llm_layer_weights(cfg, 0, 1234, "cpu", torch.float32)
-    g = torch.Generator().manual_seed(1)
-    x = torch.randn(S, cfg.hidden_size, generator=g)
+    S = total_tokens
+    hq, hkv = cfg.num_attention_heads, cfg.num_key_value_heads
+    grp = hq // hkv
+    v = cfg.visual
+    if "w" not in _REF_CACHE:
+        g = torch.Generator().manual_seed(1)
+        _REF_CACHE["w"] = llm_layer_weights(cfg, 0, 1234, "cpu", torch.float32)
+        _REF_CACHE["x"] = torch.randn(S, cfg.hidden_size, generator=g)
+        wv = global_weights(cfg, 1234, "cpu", torch.float32, with_lm=False)
+        for i in range(v.num_hidden_layers):
+            wv.update(vit_layer_weights(cfg, i, 1234, "cpu", torch.float32))
+        _REF_CACHE["wv"] = wv
+        _REF_CACHE["img"] = torch.randn(1, 3, v.image_size, v.image_size, generator=g)
+    w, x, wv, img = (_REF_CACHE[k_] for k_ in ("w", "x", "wv", "img"))
     pos = torch.arange(S)
     cos, sin = O.rope_tables(pos, O.rope_inv_freq(cfg.head_dim, cfg.rope_theta), torch.float32)
+    t_group = [0.0]
+
+    def attention_one_group(q, k, v, **kw):
+        t0 = time.perf_counter()
+        O.attention(q[:, :, :grp], k[:, :, :1], v[:, :, :1], causal=True, head_chunk=grp, q_chunk=2048)
+        t_group[0] = time.perf_counter() - t0
+        return torch.zeros(q.shape, dtype=torch.float32), None      # values are not used by a timing run
+
     t0 = time.perf_counter()
     with torch.no_grad():
-        OM.decoder_layer(cfg, w, 0, x, cos, sin)
+        OM.decoder_layer(cfg, w, 0, x, cos, sin, attention_fn=attention_one_group)
     t_layer = time.perf_counter() - t0
-    # attention alone (same shapes) to split the quadratic part
-    q = torch.randn(1, S, cfg.num_attention_heads, cfg.head_dim, generator=g)
-    k = torch.randn(1, S, cfg.num_key_value_heads, cfg.head_dim, generator=g)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        O.attention(q, k, k, causal=True)
-    t_attn = time.perf_counter() - t0
+    t_attn = t_group[0]
     t_tok = max(t_layer - t_attn, 1e-6)
-    del w
-    # vision: one frame, two layers
-    v = cfg.visual
-    wv = global_weights(cfg, 1234, "cpu", torch.float32, with_lm=False)
-    for i in range(2):
-        wv.update(vit_layer_weights(cfg, i, 1234, "cpu", torch.float32))
-    img = torch.randn(1, 3, v.image_size, v.image_size, generator=g)
+    # vision: one frame through the whole tower + projector
     t0 = time.perf_counter()
     with torch.no_grad():
-        vit = OM.vit_forward(cfg, wv, img, num_layers=2)
+        vit = OM.vit_forward(cfg, wv, img)
         OM.projector_forward(cfg, wv, vit[:, 1:, :])
-    t_vit2 = time.perf_counter() - t0
-    measured = t_layer + t_attn + t_vit2
+    t_frame = time.perf_counter() - t0
+    measured = t_layer + t_frame
     L = cfg.num_hidden_layers
-    ratio = total_tokens / S
-    t_full = L * (t_tok * ratio + t_attn * ratio * ratio) + n_frames * t_vit2 * (v.num_hidden_layers / 2.0)
-    desc = (f"oracle port (fp32, {threads} threads): 1/{L} decoder layers on {S} tokens (attention timed apart), "
-            f"1/{n_frames} frames through 2/{v.num_hidden_layers} ViT layers + projector; extrapolated "
-            f"(token-wise ~S, attention ~S^2, ViT ~frames x layers) to {total_tokens} tokens")
+    t_full = L * (t_tok + hkv * t_attn) + n_frames * t_frame
+    desc = (f"oracle port of the reference HF forward (fp32, {threads} threads), everything at the full S = {S}: "
+            f"1 of {L} decoder layers (token-wise part {t_tok:.2f} s + eager causal attention of 1 of {hkv} kv groups "
+            f"{t_attn:.2f} s) and 1 of {n_frames} frames through all {v.num_hidden_layers} ViT layers + projector "
+            f"({t_frame:.2f} s); scaled by counts of identical units only (x{L} layers, x{hkv} kv groups, x{n_frames} frames)")
     return total_tokens / t_full, measured, desc
+
+
+# ------------------------------------------------------------------------------------------------
+# probes that ride along with the bench line
+# ------------------------------------------------------------------------------------------------
+def attn_128k_probe(ops, dev, pk, launches: int = 3):
+    """Standalone `lv_attn_fwd` at the length the north-star target is quoted on (S = 131 072, 40:8 heads x 128,
+    causal): one warm-up + `launches` timed launches with CUDA events.  FLOPs are the algorithmic causal count
+    4 * Hq * d * S (S + 1) / 2.  The kernel is timed alone, so `frac` is against the measured BURST
+    cuBLAS bf16 peak; `frac_sustained` is against the sustained figure (the three launches keep the GPU busy ~0.5 s)."""
+    import torch
+
+    S, hq, hkv, d = 131072, 40, 8, 128
+    g = torch.Generator(device=dev).manual_seed(128)
+    q = torch.randn((1, S, hq, d), generator=g, device=dev, dtype=torch.bfloat16)
+    k = torch.randn((1, S, hkv, d), generator=g, device=dev, dtype=torch.bfloat16)
+    v = torch.randn((1, S, hkv, d), generator=g, device=dev, dtype=torch.bfloat16)
+    out = torch.empty_like(q)
+    ops.attention_fwd(q, k, v, causal=True, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(launches):
+        ops.attention_fwd(q, k, v, causal=True, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / launches
+    flops = 4.0 * hq * d * (S * (S + 1) / 2)
+    ach = flops / (ms / 1000.0) / 1e12
+    burst, sust = pk["bf16_tflops"], pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    return {"bound": "tensor", "kernel": "attn_fwd (standalone, S=131072, 40:8x128 causal)", "achieved": ach, "peak": burst,
+            "unit": "TFLOP/s", "frac": ach / burst, "frac_sustained": ach / sust, "frac_of_2250_datasheet": ach / 2250.0,
+            "launches": launches, "avg_launch_ms": ms, "flops_per_launch": flops,
+            "inputs": "2.7 GB Q+O, 0.5 GB K+V per launch (far beyond the 126 MB L2)"}
+
+
+def cp_parity_probe(model, runner, S, dev):
+    """Context-parallel parity inside the bench run (N > 1): the fused exchange kernel `lv_attn_cp_fwd` on this rank's
+    zig-zag rows of a random [S] problem against the single-device kernel on the all-gathered K/V with the rank's
+    query segments at their global positions (`q_seg_len` / `q_seg_pos`; that path is oracle-validated by the 1-GPU
+    tests at 16K / 128K, tests/test_gpu_attention_long.py).  Returns the worst relative Frobenius difference and
+    the worst |lse| difference over the ranks.  Layout: training/utils.py:329-341."""
+    import torch
+    import torch.distributed as dist
+
+    from long_vita_b200 import ops
+
+    cfg = model.config
+    ctx = runner._context(S, dev)
+    hq, hkv, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+    T, c = ctx.T, S // (2 * ctx.cp)
+    g = torch.Generator(device=dev).manual_seed(4321 + ctx.rank)
+    worst = torch.zeros(2, device=dev)
+    for _ in range(2):                        # both buffer parities of the exchange protocol
+        buf = ctx.qkv_buffer()                # [T, (hq + 2 hkv) d]: the fused QKV GEMM's output lives here in the model
+        buf.copy_(torch.randn(buf.shape, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16))
+        q = buf[:, : hq * d].view(T, hq, d)
+        k = buf[:, hq * d : (hq + hkv) * d].view(T, hkv, d)
+        v = buf[:, (hq + hkv) * d :].view(T, hkv, d)
+        K, V = ctx.gather_kv(k, v)            # NCCL all-gather + bit-exact re-order to global positions
+        lse_cp = torch.empty((1, hq, T), dtype=torch.float32, device=dev)
+        out_cp = ctx.attention(lse=lse_cp)
+        out_sd, lse_sd = ops.attention_fwd(q.unsqueeze(0), K.unsqueeze(0), V.unsqueeze(0), causal=True, return_lse=True,
+                                           q_seg_len=c, q_seg_pos=(ctx.rank * c, (2 * ctx.cp - 1 - ctx.rank) * c))
+        a, b = out_cp.view(T, hq * d).float(), out_sd.view(T, hq * d).float()
+        e = torch.stack([(a - b).norm() / b.norm(), (lse_cp - lse_sd).abs().max()])
+        worst = torch.maximum(worst, e)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    return float(worst[0]), float(worst[1])
+
+
+def ncu_traffic(kind: str):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py; dram__bytes_read.sum + dram__bytes_write.sum averaged
+    over the captured launches).  None when no capture is committed for that kernel."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t.get(kind)
+        return (e["dram_bytes_per_launch"], e["source"]) if e else (None, None)
+    except Exception:  # noqa: BLE001
+        return None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -170,6 +264,8 @@ def main():
     ap.add_argument("--frames", type=int, default=64, help="synthetic frames (64 -> 16K, 512 -> 128K, 4096 -> 1M)")
     ap.add_argument("--text", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cp-parity", action="store_true", help="N > 1: skip the in-run check of the fused exchange kernel")
+    ap.add_argument("--no-attn-probe", action="store_true", help="N = 1: skip the standalone 128K attention roofline probe")
     ap.add_argument("--long-run", action="store_true",
                     help="minutes-per-step configs (1M tokens): honour --warmup < 3 and skip the separate e2e pass; "
                          "the printed line is then marked as outside the timing contract")
@@ -213,15 +309,20 @@ def main():
         vals, meas = [], 0.0
         for i in range(args.warmup + args.steps):
             v, m, desc = cpu_reference_sample(cfg, S, args.frames, threads)
+            log(f"reference sample {i}: {m:.1f} s measured -> {v:.3f} tokens/s for the whole prefill")
             if i >= args.warmup:
                 vals.append(v)
                 meas += m
         value = sum(vals) / len(vals)
+        # ms_per_step = what one timed step of THIS arm really took (the bounded sample), so that steps x ms_per_step
+        # is the arm's measured time; the whole-prefill time the value corresponds to is ms_per_prefill_scaled.
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * S / value,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * meas / len(vals),
+                "ms_per_prefill_scaled": 1000.0 * S / value,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
+                                 "seconds_measured_per_step": meas / len(vals)},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return
@@ -300,6 +401,11 @@ def main():
         torch.cuda.synchronize()
         log(f"warm-up step {i} done")
     barrier()
+    cp_parity = None
+    if runner is not None and not args.no_cp_parity:
+        cp_parity = cp_parity_probe(model, runner, S, dev)
+        log(f"cp parity: out {cp_parity[0]:.3e} rel, lse {cp_parity[1]:.3e} abs")
+        barrier()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -340,7 +446,8 @@ def main():
         return {"bound": "tensor", "kernel": kind, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": f"{pk_kind} sustained cuBLAS bf16 (kernel timed inside a long step)",
                 "launches_per_step": d["launches"] / args.steps, "avg_launch_ms": d["ms"] / d["launches"],
-                "share_of_step": d["ms"] / ms_resident, "traffic": None}
+                "share_of_step": d["ms"] / ms_resident, "traffic": ncu_traffic(kind)[0], "traffic_source": ncu_traffic(kind)[1],
+                "algorithmic_bytes_or_flops_per_launch": d["flops"] / d["launches"]}
 
     dominant = max(ksum, key=lambda k_: ksum[k_]["ms"]) if ksum else None
     line = {
@@ -352,6 +459,16 @@ def main():
         "roofline": roof(dominant) if dominant else None,
         "roofline_attn": roof("attn_fwd"),
     }
+    if cp_parity is not None:
+        # fused in-kernel K/V exchange vs the single-device kernel on gathered K/V, worst rank; the run FAILS above 2e-3
+        line["cp_parity_excess"] = cp_parity[0]
+        line["cp_parity"] = {"out_rel_fro_vs_single_device": cp_parity[0], "lse_max_abs": cp_parity[1], "tokens": S,
+                             "ranks": world, "bound": 2e-3}
+        if not (cp_parity[0] < 2e-3 and cp_parity[1] < 1e-4):
+            line["INVALID"] = f"context-parallel parity failed: {cp_parity}"
+    if world == 1 and not args.no_attn_probe:
+        line["roofline_attn_128k"] = attn_128k_probe(ops, dev, pk)
+        log(f"attention @128K standalone: {line['roofline_attn_128k']['achieved']:.0f} TFLOP/s")
     if args.long_run:
         line["note"] = "--long-run: fewer than 3 warm-up steps and no separate e2e pass (minutes per step)"
     if args.layers is not None:
@@ -365,6 +482,8 @@ def main():
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if "INVALID" in line and cp_parity is not None and "parity" in line["INVALID"]:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

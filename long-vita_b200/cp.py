@@ -184,14 +184,22 @@ class CPContext(CPBackwardMixin):
     words, the local K/V staging buffers and block flags; peers' mappings opened via CUDA IPC."""
 
     _shared = {}
+    MAX_SHARED = 2     # geometries kept alive per process (e.g. the training and the evaluation sequence length)
 
     @classmethod
     def shared(cls, group, seq_total, hq, hkv, d, device, fused_qkv=True):
-        """One context per (group, geometry): all layers of a model share the buffers and the epoch."""
+        """One context per (group, geometry): all layers of a model share the buffers and the epoch.  The cache is
+        bounded: a geometry beyond MAX_SHARED evicts (and closes) the least recently used one, so prompts of varying
+        length do not pile up peer-mapped allocations (every rank makes the same calls in the same order, so every rank
+        evicts the same context - `close()` is collective)."""
         key = (id(group), seq_total, hq, hkv, d, str(device), fused_qkv)
-        if key not in cls._shared:
-            cls._shared[key] = cls(group, seq_total, hq, hkv, d, device, fused_qkv)
-        return cls._shared[key]
+        ctx = cls._shared.pop(key, None)
+        if ctx is None:
+            while len(cls._shared) >= cls.MAX_SHARED:
+                cls._shared.pop(next(iter(cls._shared))).close()
+            ctx = cls(group, seq_total, hq, hkv, d, device, fused_qkv)
+        cls._shared[key] = ctx          # most recently used last
+        return ctx
 
     def __init__(self, group, seq_total: int, hq: int, hkv: int, d: int, device, fused_qkv: bool = True):
         from . import _lib
@@ -240,17 +248,37 @@ class CPContext(CPBackwardMixin):
         self.blk_flags = torch.zeros(seq_total // 128, dtype=torch.int32, device=device)
         dist.barrier(group=group)
 
+    def close(self) -> None:
+        """Collective over the group: unmap the peers' buffers and free this rank's.  An exporter's allocation stays
+        pinned while any peer still maps it, so the order is: everyone's kernels done -> everyone closes its
+        mappings -> everyone frees.  Idempotent."""
+        if self.base is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        self.qkv = []
+        for p, ptr in enumerate(self.peer_base):
+            if p != self.rank:
+                self._check(self.lib.lv_ipc_close_handle(ptr), "lv_ipc_close_handle")
+        self.peer_base = []
+        dist.barrier(group=self.group)
+        self._check(self.lib.lv_ipc_free(self.base), "lv_ipc_free")
+        self.base = None
+        self.k_full = self.v_full = self.blk_flags = None
+
     def qkv_buffer(self) -> torch.Tensor:
         """The peer-mapped [T, row] buffer the NEXT attention call reads: the fused QKV GEMM writes
         it directly (fused_qkv) or attention_separate() copies K|V into it."""
         return self.qkv[self.epoch & 1]
 
-    def attention(self, out: Optional[torch.Tensor] = None, scale: Optional[float] = None) -> torch.Tensor:
+    def attention(self, out: Optional[torch.Tensor] = None, scale: Optional[float] = None,
+                  lse: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Causal attention of the local queries (already RoPE'd, inside qkv_buffer()) over the whole
-        sequence; K/V of the other ranks are pulled by the kernel.  Returns [T, hq*d]."""
+        sequence; K/V of the other ranks are pulled by the kernel.  Returns [T, hq*d]; `lse` ([1, hq, T] fp32,
+        optional) receives the log-sum-exp."""
         assert self.fused_qkv
         buf = self.qkv[self.epoch & 1]
-        return self._launch(buf.data_ptr(), (self.T * self.row, self.row, self.d), out, scale)
+        return self._launch(buf.data_ptr(), (self.T * self.row, self.row, self.d), out, scale, lse)
 
     def attention_separate(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out=None, scale=None,
                            return_lse: bool = False):
@@ -326,8 +354,15 @@ class ContextParallelRunner:
     def _context(self, S: int, device) -> CPContext:
         cfg = self.model.config
         if self.ctx is None or self.ctx.S != S:
+            if self.ctx is not None:
+                self.ctx.close()       # a new prompt length: release the peer-mapped buffers of the old one first
             self.ctx = CPContext(self.group, S, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, device)
         return self.ctx
+
+    def close(self) -> None:
+        if self.ctx is not None:
+            self.ctx.close()
+            self.ctx = None
 
     def forward(self, input_ids: torch.Tensor, images: Optional[torch.Tensor], image_indices: Optional[torch.Tensor],
                 gather_logits: bool = True, use_cache: bool = False, max_new_tokens: int = 1024) -> torch.Tensor:

@@ -815,13 +815,14 @@ static int launch_bwd(const lv_attn_bwd_params* a, cudaStream_t s) {
   p.n_kt = (int)((f->sk + 127) / 128);
   p.lse = f->lse;
   p.delta = a->delta_ws;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  int attr_dev;
+  if (attr_once.needed(&attr_dev)) {
     LV_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     LV_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     LV_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     LV_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   // LV_BWD_VERSION=2: the warp-specialised, pipelined kernel (same arithmetic; see attn_bwd2_kernel)
   static const int version = [] {

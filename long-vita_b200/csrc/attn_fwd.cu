@@ -1165,14 +1165,15 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
     return (e != nullptr && e[0] == '0') ? 0 : 1;
   }();
   p.serpentine = serp;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;   // one per template instantiation
+  int attr_dev;
+  if (attr_once.needed(&attr_dev)) {
     if constexpr (VER == 2) {
       LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<D, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     } else {
       LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, QH, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     }
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   int grid = p.n_items < sm_count() ? p.n_items : sm_count();
   CpKParams cpp;

@@ -8,6 +8,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "../../include/lvb200.h"
 
 namespace lv {
@@ -18,6 +20,26 @@ int sm_count();
 // Make the device that owns `ptr` current on the calling thread (autograd runs backward on its own
 // threads, which may have no current CUDA context yet).  Returns LV_OK or LV_ECUDA.
 int bind_device(const void* ptr);
+
+// One-time per-DEVICE setup of a call site (cudaFuncSetAttribute is a per-device property and the library serves
+// several devices from one process, possibly from several threads: a per-process `static bool` would leave the
+// second GPU with the 48 KB default and race).  Usage: static PerDeviceOnce once; int dev; if (once.needed(&dev))
+// { ...setup...; once.done(dev); }   A concurrent duplicate setup is harmless (the attributes are idempotent).
+class PerDeviceOnce {
+  std::atomic<int> done_[64] = {};
+
+ public:
+  bool needed(int* dev) {
+    if (cudaGetDevice(dev) != cudaSuccess || *dev < 0 || *dev >= 64) {
+      *dev = -1;
+      return true;   // unknown device: set the attributes on every call
+    }
+    return done_[*dev].load(std::memory_order_acquire) == 0;
+  }
+  void done(int dev) {
+    if (dev >= 0) done_[dev].store(1, std::memory_order_release);
+  }
+};
 
 // Encode a bf16 tiled tensor map.  dims/strides innermost-first; strides in BYTES for dims 1..rank-1
 // (dim 0 is contiguous).  box = tile extents, innermost-first.  swizzle128: 128-byte swizzle

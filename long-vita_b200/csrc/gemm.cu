@@ -483,10 +483,11 @@ static int launch_gemm(const void* A, const void* W, const void* bias, void* C, 
     int r = encode_tmap_bf16(&tmC, C, 2, dims, str, box, true);
     if (r) return r;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  int attr_dev;
+  if (attr_once.needed(&attr_dev)) {
     LV_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   const int64_t tiles = ((M + G_BM - 1) / G_BM) * ((N + G_BN - 1) / G_BN);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());

@@ -85,12 +85,13 @@ class B200DotProductAttention(torch.nn.Module):
     def _cp(self, query, key):
         if self.cp_size <= 1 or not _is_causal(self.attn_mask_type):
             return None
-        if self._cp_ctx is None:
+        sq, _, np_, hn = query.shape
+        if self._cp_ctx is None or self._cp_ctx.S != sq * self.cp_size:
+            # keyed on the sequence length of THIS call: a later micro-batch of another length gets its own buffers
             from megatron.core import parallel_state as mpu   # only reached inside a Megatron job
 
             from ..cp import CPContext
 
-            sq, _, np_, hn = query.shape
             self._cp_ctx = CPContext.shared(mpu.get_context_parallel_group(), sq * self.cp_size, np_, key.shape[2], hn,
                                             query.device, fused_qkv=False)
         return self._cp_ctx

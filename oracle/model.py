@@ -83,8 +83,9 @@ def projector_forward(cfg, w, vit_tokens_no_cls, prefix="model.vision_projection
 # Qwen2 decoder
 # ------------------------------------------------------------------------------------------------
 def decoder_layer(cfg, w, i: int, x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor,
-                  q_pos: Optional[torch.Tensor] = None, kv_pos: Optional[torch.Tensor] = None):
-    """One Qwen2 decoder layer on x [s, H] (batch 1), cos/sin [s, head_dim] in x.dtype."""
+                  q_pos: Optional[torch.Tensor] = None, kv_pos: Optional[torch.Tensor] = None, attention_fn=None):
+    """One Qwen2 decoder layer on x [s, H] (batch 1), cos/sin [s, head_dim] in x.dtype.  `attention_fn` (default
+    `oracle.ops.attention`) lets bench.py's CPU leg time the attention of one kv group apart from the token-wise part."""
     p = f"model.layers.{i}."
     s = x.shape[0]
     hq, hkv, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
@@ -93,7 +94,7 @@ def decoder_layer(cfg, w, i: int, x: torch.Tensor, cos: torch.Tensor, sin: torch
     k = F.linear(h, w[p + "self_attn.k_proj.weight"], w[p + "self_attn.k_proj.bias"]).view(s, hkv, d)
     v = F.linear(h, w[p + "self_attn.v_proj.weight"], w[p + "self_attn.v_proj.bias"]).view(s, hkv, d)
     q, k = O.rope_apply(q, cos, sin), O.rope_apply(k, cos, sin)
-    att, _ = O.attention(q[None], k[None], v[None], causal=True, q_pos=q_pos, kv_pos=kv_pos)
+    att, _ = (attention_fn or O.attention)(q[None], k[None], v[None], causal=True, q_pos=q_pos, kv_pos=kv_pos)
     att = att[0].to(x.dtype).reshape(s, hq * d)
     x = x + F.linear(att, w[p + "self_attn.o_proj.weight"])
     h = O.rmsnorm(x, w[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps)

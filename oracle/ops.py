@@ -42,6 +42,7 @@ def attention(
     q_pos: Optional[torch.Tensor] = None,
     kv_pos: Optional[torch.Tensor] = None,
     head_chunk: int = 8,
+    q_chunk: Optional[int] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """softmax(scale q k^T + mask) v in fp32 with its log-sum-exp.
 
@@ -51,8 +52,19 @@ def attention(
     q [b, sq, hq, d], k/v [b, sk, hkv, d] (any float dtype; math in fp32).  `q_pos` / `kv_pos` are
     global positions (int64 [sq] / [sk]); causal masks keys with kv_pos > q_pos.  Defaults give the
     bottom-right aligned mask of flash-attn >= 2.1.  Returns (out [b, sq, hq, d] fp32,
-    lse [b, hq, sq] fp32)."""
+    lse [b, hq, sq] fp32).  `head_chunk` / `q_chunk` only bound the size of the score matrix held at once
+    (rows of a softmax are independent; the arithmetic per row is unchanged)."""
     b, sq, hq, d = q.shape
+    if q_chunk is not None and q_chunk < sq:
+        if q_pos is None:
+            q_pos = torch.arange(sq, dtype=torch.int64) + (k.shape[1] - sq)
+        outs, lses = [], []
+        for r0 in range(0, sq, q_chunk):
+            o, l = attention(q[:, r0 : r0 + q_chunk], k, v, causal=causal, scale=scale, q_pos=q_pos[r0 : r0 + q_chunk],
+                             kv_pos=kv_pos, head_chunk=head_chunk)
+            outs.append(o)
+            lses.append(l)
+        return torch.cat(outs, dim=1), torch.cat(lses, dim=2)
     sk, hkv = k.shape[1], k.shape[2]
     g = hq // hkv
     scale = 1.0 / math.sqrt(d) if scale is None else scale
