@@ -1158,6 +1158,11 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
   p.n_items = (int)(a->batch * a->hq * p.n_qblk);
   // all kv heads' K and V fit comfortably in the 126 MB L2 -> global longest-first order
   p.block_major = (a->causal && a->sk * a->hkv * a->d * 4 <= (64ll << 20)) ? 1 : 0;
+  static const int order_env = [] {   // LV_ATTN_ORDER=0 / 1 forces head-major / block-major order (A/B runs)
+    const char* e = getenv("LV_ATTN_ORDER");
+    return (e != nullptr && (e[0] == '0' || e[0] == '1')) ? (e[0] - '0') : -1;
+  }();
+  if (order_env >= 0 && a->causal) p.block_major = order_env;
   p.lse = a->lse;
   p.poly_exp = attn_poly_exp();
   static const int serp = [] {

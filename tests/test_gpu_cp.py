@@ -79,6 +79,12 @@ def _worker(rank, world, port):
             e_floor = _rel(ref_l.to(torch.bfloat16), ref_l)
             assert math.sqrt(max(e * e - e_floor * e_floor, 0.0)) < 2e-3, (rank, epoch, e, e_floor)
         dist.barrier()
+        # release the peer-mapped buffers (collective): mappings closed on every rank, then the allocations freed
+        free0 = torch.cuda.mem_get_info(dev)[0]
+        ctx.close()
+        ctx2.close()
+        ctx.close()      # idempotent
+        assert ctx.base is None and torch.cuda.mem_get_info(dev)[0] >= free0
 
         # ---- whole sharded prefill vs the single-device forward ----
         cfg = LongVITAConfig.tiny(layers=3, vit_layers=1)
