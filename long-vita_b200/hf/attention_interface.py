@@ -29,9 +29,21 @@ def b200_attention_forward(module, query, key, value, attention_mask=None, dropo
         raise NotImplementedError("attention dropout is not supported by the fused kernel")
     if kwargs.get("sliding_window") not in (None, 0) and kwargs["sliding_window"] < key.shape[2]:
         raise NotImplementedError("sliding-window attention is not used by Long-VITA (use_sliding_window=false)")
-    if attention_mask is not None and attention_mask.dtype != torch.bool and attention_mask.dim() == 2 \
-            and not bool(attention_mask.to(torch.bool).all()):
-        raise NotImplementedError("padding masks are not supported; pass unpadded sequences")
+    if attention_mask is not None:
+        # The fused kernel applies the causal (or no) mask itself; any OTHER masking must be refused, not ignored.
+        if attention_mask.dim() == 2:                       # [b, sk] key-padding mask (flash_attention_2 style)
+            if not bool(attention_mask.to(torch.bool).all()):
+                raise NotImplementedError("padding masks are not supported; pass unpadded sequences (batch 1)")
+        elif attention_mask.dim() == 4:
+            # [b, 1, sq, sk] masks transformers builds for sdpa / eager: bool (True = attend) or additive (0 = attend).
+            # Pure causal <=> the LAST query row attends to every key (a padded key column would be masked there too).
+            last = attention_mask[:, :, -1, :]
+            visible = last if attention_mask.dtype == torch.bool else (last == 0)
+            if not bool(visible.all()):
+                raise NotImplementedError("b200_fa: the 4-D attention mask hides keys from the last query (padding or a "
+                                          "custom mask); only pure causal / full attention on unpadded inputs is supported")
+        else:
+            raise NotImplementedError(f"b200_fa: unsupported attention_mask rank {attention_mask.dim()}")
     if is_causal is None:
         is_causal = bool(getattr(module, "is_causal", True)) and query.shape[2] > 1
     out = ops.attention_fwd(query, key, value, causal=is_causal, scale=scaling, layout="bhsd")   # [b,h,s,d]

@@ -203,8 +203,44 @@ class DecoderLayer:
         return x, ops.linear(a, self.w_down)
 
 
-class LongVITAModel:
+def _map_tensors(obj, fn, seen=None):
+    """Apply `fn` to every tensor reachable from the attributes of our plain weight holders (in place)."""
+    seen = set() if seen is None else seen
+    if id(obj) in seen:
+        return
+    seen.add(id(obj))
+    items = obj.items() if isinstance(obj, dict) else vars(obj).items()
+    for name, val in list(items):
+        if isinstance(val, torch.Tensor):
+            new = fn(val)
+            if isinstance(obj, dict):
+                obj[name] = new
+            else:
+                object.__setattr__(obj, name, new)
+        elif isinstance(val, (list, tuple)):
+            for i, e in enumerate(val):
+                if isinstance(e, torch.Tensor):
+                    val[i] = fn(e)
+                elif isinstance(e, (dict, InternVisionModel, ResamplerProjector, DecoderLayer)):
+                    _map_tensors(e, fn, seen)
+        elif isinstance(val, (dict, InternVisionModel, ResamplerProjector, DecoderLayer)):
+            _map_tensors(val, fn, seen)
+
+
+class _WeightHolderModule(torch.nn.Module):
+    """nn.Module whose weights live in plain tensors (fused / re-laid-out once at load for the kernels) rather than in
+    nn.Parameters: `.to()` / `.cuda()` / `.eval()` / hooks work as for any module, `state_dict()` is rebuilt in the
+    reference's HF names by the subclasses."""
+
+    def _apply(self, fn, recurse=True):
+        super()._apply(fn, recurse)
+        _map_tensors(self, lambda t: fn(t) if t.is_floating_point() or t.dtype in (torch.int64, torch.int32) else t)
+        return self
+
+
+class LongVITAModel(_WeightHolderModule):
     def __init__(self, cfg: LongVITAConfig, weights: Dict[str, torch.Tensor]):
+        super().__init__()
         self.config = cfg
         self.embed_tokens = weights["model.embed_tokens.weight"]
         self.norm_w = weights["model.norm.weight"]
@@ -303,14 +339,107 @@ class LongVITAModel:
         out = BaseOutput(last_hidden_state=h, past_key_values=cache, hidden_states=all_hidden)
         return out if (return_dict is None or return_dict) else out.to_tuple()
 
-    __call__ = forward
+    def hf_state_dict(self, prefix: str = "model.") -> Dict[str, torch.Tensor]:
+        """The weights under the reference's HF parameter names (views of the fused buffers; the padded patch-embed
+        operand is cut back to the [C, 3, ps, ps] conv weight)."""
+        sd = {prefix + "embed_tokens.weight": self.embed_tokens, prefix + "norm.weight": self.norm_w}
+        cfg = self.config
+        for i, L in enumerate(self.layers):
+            p = f"{prefix}layers.{i}."
+            q, kv = cfg.q_size, cfg.kv_size
+            sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.q_proj.bias"] = L.wqkv[:q], L.bqkv[:q]
+            sd[p + "self_attn.k_proj.weight"], sd[p + "self_attn.k_proj.bias"] = L.wqkv[q : q + kv], L.bqkv[q : q + kv]
+            sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.v_proj.bias"] = L.wqkv[q + kv :], L.bqkv[q + kv :]
+            sd[p + "self_attn.o_proj.weight"] = L.wo
+            sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"] = L.w_gate_up[0::2], L.w_gate_up[1::2]
+            sd[p + "mlp.down_proj.weight"] = L.w_down
+            sd[p + "input_layernorm.weight"], sd[p + "post_attention_layernorm.weight"] = L.ln1, L.ln2
+        if self.vision_model is not None:
+            v, vm = cfg.visual, self.vision_model
+            e = prefix + "vision_model.embeddings."
+            sd[e + "class_embedding"], sd[e + "position_embedding"] = vm.cls, vm.pos
+            k = 3 * v.patch_size * v.patch_size
+            sd[e + "patch_embedding.weight"] = vm.patch_w[:, :k].reshape(-1, 3, v.patch_size, v.patch_size)
+            sd[e + "patch_embedding.bias"] = vm.patch_b
+            for i, L in enumerate(vm.layers):
+                for name, t in L.items():
+                    sd[f"{prefix}vision_model.encoder.layers.{i}.{name}"] = t
+            pj = self.vision_projection
+            q = prefix + "vision_projection."
+            sd[q + "pre_proj_layernorm.weight"], sd[q + "pre_proj_layernorm.bias"] = pj.ln_w, pj.ln_b
+            sd[q + "mlp.0.weight"], sd[q + "mlp.2.weight"] = pj.w0, pj.w2
+        return sd
 
 
-class LongVITAForCausalLM:
+class GenerationDefaults:
+    """The fields of transformers' GenerationConfig this build reads; `model.generation_config` may be replaced by a
+    real GenerationConfig (tools/inference_long_vita.py:819-826 assigns one and then sets these attributes)."""
+
+    def __init__(self):
+        self.max_new_tokens = 1024
+        self.do_sample = False
+        self.use_cache = True
+        self.eos_token_id = None
+        self.pad_token_id = None
+
+
+class LongVITAForCausalLM(_WeightHolderModule):
     def __init__(self, cfg: LongVITAConfig, weights: Dict[str, torch.Tensor]):
+        super().__init__()
         self.config = cfg
         self.model = LongVITAModel(cfg, weights)
         self.lm_head = weights["lm_head.weight"]
+        self.generation_config = GenerationDefaults()
+
+    @property
+    def device(self) -> torch.device:
+        return self.lm_head.device
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.lm_head.dtype
+
+    def state_dict(self, *args, **kwargs) -> Dict[str, torch.Tensor]:
+        sd = self.model.hf_state_dict("model.")
+        sd["lm_head.weight"] = self.lm_head
+        return sd
+
+    @classmethod
+    def from_pretrained(cls, model_path: str, torch_dtype=torch.bfloat16, device_map=None, attn_implementation=None,
+                        trust_remote_code: bool = True, **kwargs):
+        """Load a Long-VITA HF checkpoint directory (config.json + *.safetensors shards), the call
+        tools/inference_long_vita.py:811-817 makes through AutoModelForCausalLM.  Only bfloat16 runs on the fused
+        path; `attn_implementation` is accepted and ignored (the fused kernel IS the attention implementation);
+        `device_map` "auto" / None -> the current CUDA device."""
+        import glob
+        import json
+        import os
+
+        from safetensors import safe_open
+
+        if torch_dtype not in (torch.bfloat16, "bfloat16", None, "auto"):
+            raise NotImplementedError("the fused path computes in bfloat16 (the reference's torch_dtype)")
+        c = json.load(open(os.path.join(model_path, "config.json")))
+        vc = c.get("visual", c.get("vision_config", {})) or {}
+        from dataclasses import fields, replace
+
+        from ..config import VisionConfig
+
+        def pick(dc, src):
+            names = {f.name for f in fields(dc)}
+            return {k: v for k, v in src.items() if k in names and not isinstance(v, dict)}
+
+        cfg = replace(LongVITAConfig(**pick(LongVITAConfig, c)), visual=VisionConfig(**pick(VisionConfig, vc)))
+        dev = torch.device("cuda", torch.cuda.current_device()) if device_map in (None, "auto") else torch.device(device_map)
+        w: Dict[str, torch.Tensor] = {}
+        shards = sorted(glob.glob(os.path.join(model_path, "*.safetensors")))
+        if not shards:
+            raise FileNotFoundError(f"no *.safetensors under {model_path}")
+        for sh in shards:
+            with safe_open(sh, framework="pt", device=str(dev)) as f:
+                for name in f.keys():
+                    w[name] = f.get_tensor(name).to(torch.bfloat16)
+        return cls(cfg, w)
 
     @classmethod
     def from_synthetic(cls, cfg: LongVITAConfig, seed: int = 1234, device="cuda", perturb: bool = False,
@@ -324,9 +453,12 @@ class LongVITAForCausalLM:
             w.update(vit_layer_weights(cfg, i, seed, device, torch.bfloat16, perturb))
         n_layers = cfg.num_hidden_layers if num_layers is None else num_layers
         self = cls.__new__(cls)
+        torch.nn.Module.__init__(self)
         self.config = cfg
         self.lm_head = w["lm_head.weight"]
+        self.generation_config = GenerationDefaults()
         model = LongVITAModel.__new__(LongVITAModel)
+        torch.nn.Module.__init__(model)
         model.config = cfg
         model.embed_tokens = w["model.embed_tokens.weight"]
         model.norm_w = w["model.norm.weight"]
@@ -381,16 +513,44 @@ class LongVITAForCausalLM:
                              hidden_states=outputs.hidden_states)
         return out if (return_dict is None or return_dict) else out.to_tuple()
 
-    __call__ = forward
+    @torch.no_grad()
+    def generate(self, inputs: Optional[torch.Tensor] = None, images: Optional[torch.Tensor] = None,
+                 image_indices: Optional[torch.Tensor] = None, generation_config=None, input_ids: Optional[torch.Tensor] = None,
+                 max_new_tokens: Optional[int] = None, eos_token_id=None, do_sample: Optional[bool] = None, **kwargs):
+        """`model.generate(inputs=, images=, image_indices=)` as tools/inference_long_vita.py:868 calls it: greedy
+        decoding (the script sets do_sample = False) with the K/V cache; stops at `eos_token_id` (int or list) or after
+        `max_new_tokens`; returns prompt + generated ids [1, s + n] like transformers' GenerationMixin.  Inputs on the
+        host are moved to the model's device (the script leaves them on the CPU under device_map="auto")."""
+        gc = generation_config if generation_config is not None else self.generation_config
+        ids = inputs if inputs is not None else input_ids
+        if ids is None:
+            raise ValueError("generate() needs `inputs` (token ids [1, s])")
+        sample = getattr(gc, "do_sample", False) if do_sample is None else do_sample
+        if sample or kwargs.get("num_beams", 1) not in (None, 1):
+            raise NotImplementedError("greedy decoding only (the reference's inference script: do_sample = False)")
+        n_new = max_new_tokens if max_new_tokens is not None else (getattr(gc, "max_new_tokens", None) or 1024)
+        eos = eos_token_id if eos_token_id is not None else getattr(gc, "eos_token_id", None)
+        eos = set() if eos is None else ({int(eos)} if isinstance(eos, int) else {int(e) for e in eos})
+        dev = self.device
+        ids = ids.to(dev)
+        if images is not None:
+            images = images.to(dev, dtype=torch.bfloat16)
+        if image_indices is not None:
+            image_indices = image_indices.to(dev)
+        new = self.generate_greedy(ids, images, image_indices, max_new_tokens=int(n_new), eos_token_ids=eos)
+        return torch.cat([ids, new], dim=1)
 
     @torch.no_grad()
     def generate_greedy(self, input_ids: torch.Tensor, images: Optional[torch.Tensor] = None,
                         image_indices: Optional[torch.Tensor] = None, max_new_tokens: int = 16,
-                        eos_token_id: Optional[int] = None) -> torch.Tensor:
+                        eos_token_id: Optional[int] = None, eos_token_ids=None) -> torch.Tensor:
         """Greedy decoding with the K/V cache: one prefill, then one forward per token over a single new
         row (the reference's Megatron loop feeds the whole sequence again for every token,
         generation.py:127-135).  Returns the generated ids [1, n]."""
         s = input_ids.shape[1]
+        stop = set(eos_token_ids or ())
+        if eos_token_id is not None:
+            stop.add(int(eos_token_id))
         out = self.forward(input_ids=input_ids, images=images, image_indices=image_indices, use_cache=True,
                            num_logits_to_keep=1, max_cache_len=s + max_new_tokens)
         cache = out.past_key_values
@@ -398,7 +558,7 @@ class LongVITAForCausalLM:
         tok = out.logits[0, -1].float().argmax().view(1, 1)
         for _ in range(max_new_tokens):
             new.append(tok)
-            if eos_token_id is not None and int(tok) == eos_token_id:
+            if stop and int(tok) in stop:
                 break
             if len(new) == max_new_tokens:
                 break

@@ -73,9 +73,16 @@ class B200TransformerLayer(torch.nn.Module):
         self.mlp.linear_fc1.weight = P(2 * ffn, h)
         self.mlp.linear_fc2 = _Params()
         self.mlp.linear_fc2.weight = P(h, ffn)
-        self._qkv_w = None       # re-ordered copies, built on first forward
+        self._qkv_w = None       # re-ordered copies of the parameters, rebuilt whenever a parameter changes
         self._qkv_b = None
+        self._fused_versions = None
         self._rope_cache = (None, None, None)
+        if int(getattr(config, "tensor_model_parallel_size", 1) or 1) > 1:
+            raise NotImplementedError("B200TransformerLayer holds whole weights: tensor_model_parallel_size must be 1 "
+                                      "(14B bf16 fits one B200; the BASELINE configs are CP x DP)")
+        self.cp_size = int(getattr(config, "context_parallel_size", 1) or 1)
+        self._cp_ctx = None
+        self.cp_group = getattr(config, "cp_group", None)   # tests / Megatron-free callers may hand the group in
 
     # -- Megatron grouped QKV rows -> [q | k | v] -------------------------------------------------
     def _ungroup(self):
@@ -88,6 +95,33 @@ class B200TransformerLayer(torch.nn.Module):
         self._qkv_b = torch.cat([b[:, :g].reshape(-1), b[:, g].reshape(-1), b[:, g + 1].reshape(-1)]).contiguous()
         fc1 = self.mlp.linear_fc1.weight.data                      # cat(gate, up) -> rows (gate_i, up_i)
         self._fc1_w = ops.interleave_gate_up(fc1[: self.ffn], fc1[self.ffn :])
+
+    def _fused_weights_current(self) -> bool:
+        """The re-ordered copies follow load_state_dict() / optimizer steps: every in-place update of a parameter bumps
+        its `_version`, and a re-assigned `.data` changes `data_ptr()`."""
+        ps = (self.self_attention.linear_qkv.weight, self.self_attention.linear_qkv.bias, self.mlp.linear_fc1.weight)
+        stamp = tuple((p._version, p.data_ptr()) for p in ps)
+        if self._qkv_w is None or stamp != self._fused_versions:
+            self._ungroup()
+            self._fused_versions = stamp
+        return True
+
+    def _cp(self, s: int, device):
+        """Context parallelism (zig-zag shards, training/utils.py:329-341): the layer receives this rank's rows only,
+        so attention must see the other ranks' K/V - `cp.CPContext` (fused in-kernel exchange forward, all-gather /
+        reduce-scatter backward).  None when context_parallel_size == 1."""
+        if self.cp_size <= 1:
+            return None
+        if self._cp_ctx is None or self._cp_ctx.S != s * self.cp_size:
+            from ..cp import CPContext
+
+            group = self.cp_group
+            if group is None:
+                from megatron.core import parallel_state as mpu   # only reached inside a Megatron job
+
+                group = mpu.get_context_parallel_group()
+            self._cp_ctx = CPContext.shared(group, s * self.cp_size, self.np, self.ng, self.hn, device, fused_qkv=False)
+        return self._cp_ctx
 
     def _rope(self, rotary_pos_emb):
         """Megatron hands the layer `freqs` [s, 1, 1, hn] fp32 (rotary_pos_embedding.py:84-122); the
@@ -111,8 +145,7 @@ class B200TransformerLayer(torch.nn.Module):
             raise NotImplementedError("micro-batch 1 (the reference's long-context setting)")
         if torch.is_grad_enabled() and (hidden_states.requires_grad or any(p.requires_grad for p in self.parameters())):
             return self._forward_train(hidden_states, rotary_pos_emb), context
-        if self._qkv_w is None:
-            self._ungroup()
+        self._fused_weights_current()
         np_, ng, hn = self.np, self.ng, self.hn
         x = hidden_states.reshape(s, h)
         hcur = ops.rmsnorm(x, self.self_attention.linear_qkv.layer_norm_weight, self.eps)
@@ -124,7 +157,11 @@ class B200TransformerLayer(torch.nn.Module):
             cos, sin = self._rope(rotary_pos_emb)
             ops.rope(q, cos, sin, out=q)
             ops.rope(k, cos, sin, out=k)
-        att = ops.attention_fwd(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), causal=True)
+        cp_ctx = self._cp(s, hidden_states.device)
+        if cp_ctx is not None:
+            att = cp_ctx.attention_separate(q, k, v)                               # [s, np * hn]
+        else:
+            att = ops.attention_fwd(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), causal=True)
         o = ops.linear(att.view(s, np_ * hn), self.self_attention.linear_proj.weight)
         hcur, x = ops.rmsnorm(o, self.mlp.linear_fc1.layer_norm_weight, self.eps, residual=x)
         a = ops.linear(hcur, self._fc1_w, act="swiglu")
@@ -155,7 +192,13 @@ class B200TransformerLayer(torch.nn.Module):
             cos, sin = self._rope(rotary_pos_emb)
             q = ops.rope_autograd(q, cos, sin)
             k = ops.rope_autograd(k, cos, sin)
-        att = ops.attention(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), causal=True)       # [1, s, np, hn]
+        cp_ctx = self._cp(s, hidden_states.device)
+        if cp_ctx is not None:
+            from ..cp import cp_attention
+
+            att = cp_attention(q.contiguous(), k, v, cp_ctx)                                    # [s, np * hn]
+        else:
+            att = ops.attention(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), causal=True)   # [1, s, np, hn]
         o = ops.linear_autograd(att.reshape(s, np_ * hn), a.linear_proj.weight)
         hcur, x = ops.rmsnorm_autograd(o, self.mlp.linear_fc1.layer_norm_weight, self.eps, residual=x)
         gate_up = ops.linear_autograd(hcur, self.mlp.linear_fc1.weight)                         # cat(gate, up)

@@ -203,3 +203,61 @@ def test_kv_cache_decode_against_the_references_own_incremental_decoding():
             assert rel_fro(o.logits[0, 0], dec["steps"][i]) < 2e-2, (i, rel_fro(o.logits[0, 0], dec["steps"][i]))
             assert int(o.logits[0, 0].float().argmax()) == int(dec["steps"][i].argmax())
         assert len(cache) == dec["cache_len"]
+
+
+# ---- the surface tools/inference_long_vita.py:811-868 uses: nn.Module, from_pretrained, generation_config, generate ----
+def test_model_is_a_module_with_the_reference_state_dict(setup):
+    cfg, w, model, _ = setup
+    assert isinstance(model, torch.nn.Module) and isinstance(model.model, torch.nn.Module)
+    assert model.eval() is model and model.dtype == torch.bfloat16 and model.device.type == "cpu"
+    sd = model.state_dict()
+    assert set(sd) == set(w), (set(sd) ^ set(w))
+    for k_, t in w.items():                       # fused / interleaved / padded buffers un-fuse to the HF tensors bit for bit
+        assert sd[k_].shape == t.shape and torch.equal(sd[k_], t), k_
+
+
+def test_from_pretrained_reads_an_hf_checkpoint_directory(setup, tmp_path):
+    import dataclasses
+    import json
+
+    from safetensors.torch import save_file
+
+    cfg, w, model, _ = setup
+    c = {f.name: getattr(cfg, f.name) for f in dataclasses.fields(cfg) if f.name != "visual"}
+    c["visual"] = dataclasses.asdict(cfg.visual)
+    c["architectures"] = ["LongVITAForCausalLM"]
+    (tmp_path / "config.json").write_text(json.dumps(c))
+    names = sorted(w)
+    save_file({k_: w[k_].contiguous() for k_ in names[::2]}, str(tmp_path / "model-00001-of-00002.safetensors"))
+    save_file({k_: w[k_].contiguous() for k_ in names[1::2]}, str(tmp_path / "model-00002-of-00002.safetensors"))
+    m2 = LongVITAForCausalLM.from_pretrained(str(tmp_path), trust_remote_code=True, device_map="cpu", torch_dtype=torch.bfloat16,
+                                             attn_implementation="flash_attention_2")
+    assert m2.config == cfg
+    sd = m2.state_dict()
+    assert all(torch.equal(sd[k_], w[k_]) for k_ in w)
+    with pytest.raises(NotImplementedError):
+        LongVITAForCausalLM.from_pretrained(str(tmp_path), torch_dtype=torch.float16, device_map="cpu")
+
+
+def test_generate_follows_the_inference_script_contract(setup):
+    cfg, w, model, w32 = setup
+    ids, images, idx = _inputs(cfg, s=290)
+    model.generation_config.max_new_tokens = 4          # the script mutates model.generation_config in place (:821-826)
+    model.generation_config.do_sample = False
+    with oracle_ops():
+        out = model.generate(inputs=ids, images=images, image_indices=idx)
+        first = model(input_ids=ids, images=images, image_indices=idx, num_logits_to_keep=1).logits[0, -1].float().argmax()
+        stop = model.generate(inputs=ids, images=images, image_indices=idx, eos_token_id=[int(out[0, 290]), 7])
+    assert out.shape == (1, 294) and torch.equal(out[:, :290], ids)          # prompt + new tokens, like GenerationMixin
+    assert int(out[0, 290]) == int(first)
+    assert stop.shape == (1, 291)                                            # stops AT the eos token (kept, as in HF)
+    # greedy continuation equals re-running the full forward on the grown sequence (cache == no cache)
+    seq = ids
+    with oracle_ops():
+        for i in range(3):
+            nxt = model(input_ids=seq, images=images, image_indices=idx, num_logits_to_keep=1).logits[0, -1].float().argmax()
+            assert int(nxt) == int(out[0, 290 + i])
+            seq = torch.cat([seq, nxt.view(1, 1)], dim=1)
+    with pytest.raises(NotImplementedError):
+        model.generate(inputs=ids, do_sample=True)
+    model.generation_config.max_new_tokens = 1024

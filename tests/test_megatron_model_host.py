@@ -193,6 +193,24 @@ def test_spec_layer_ungroups_megatron_weights(tiny):
     cos, sin = O.rope_tables(torch.arange(s), inv, torch.float32)
     ref = OM.decoder_layer(cfg, OM.cast_weights(hf, torch.float32), 0, x[:, 0].float(), cos, sin)
     assert rel_fro(out[:, 0], ref) < 6e-3, rel_fro(out[:, 0], ref)
+    # weights updated AFTER the first forward (load_state_dict / an optimizer step) must reach the re-ordered copies
+    sd2 = {k_: (v * 0.5 if k_.endswith("linear_fc1.weight") else v) for k_, v in sd.items()}
+    layer.load_state_dict(sd2, strict=True)
+    hf2 = dict(hf)
+    for n_ in ("gate_proj", "up_proj"):
+        hf2[f"model.layers.0.mlp.{n_}.weight"] = hf[f"model.layers.0.mlp.{n_}.weight"] * 0.5
+    with oracle_ops():
+        out2, _ = layer(hidden_states=x, rotary_pos_emb=rotary)
+    ref2 = OM.decoder_layer(cfg, OM.cast_weights(hf2, torch.float32), 0, x[:, 0].float(), cos, sin)
+    assert rel_fro(out2[:, 0], ref2) < 6e-3 and not torch.equal(out2, out)
+    with torch.no_grad():
+        layer.self_attention.linear_qkv.bias.add_(0.25)          # in-place update: caught through the version counter
+    with oracle_ops():
+        out3, _ = layer(hidden_states=x, rotary_pos_emb=rotary)
+    assert not torch.equal(out3, out2)
+    # whole weights only
+    with pytest.raises(NotImplementedError, match="tensor_model_parallel_size"):
+        B200TransformerLayer(types.SimpleNamespace(**{**vars(mcfg), "tensor_model_parallel_size": 2}), layer_number=1)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -84,6 +84,19 @@ def test_hf_attention_interface_function_layout_and_guards():
         AI.b200_attention_forward(None, q, k, v, None, sliding_window=16)
     with pytest.raises(NotImplementedError):
         AI.b200_attention_forward(None, q, k, v, torch.tensor([[1] * 79 + [0], [1] * 80]))
+    # 4-D masks (what transformers builds for sdpa / eager): pure causal passes, a padded key column is refused
+    causal4 = torch.tril(torch.ones(80, 80, dtype=torch.bool))[None, None].expand(2, 1, 80, 80)
+    additive = torch.zeros(2, 1, 80, 80).masked_fill(~causal4, float("-inf"))
+    with oracle_ops():
+        o_bool, _ = AI.b200_attention_forward(None, q, k, v, causal4, scaling=0.2, is_causal=True)
+        o_add, _ = AI.b200_attention_forward(None, q, k, v, additive, scaling=0.2, is_causal=True)
+    assert torch.equal(o_bool, out) and torch.equal(o_add, out)
+    padded = causal4.clone()
+    padded[1, :, :, 0] = False
+    with pytest.raises(NotImplementedError, match="4-D attention mask"):
+        AI.b200_attention_forward(None, q, k, v, padded, scaling=0.2, is_causal=True)
+    with pytest.raises(NotImplementedError, match="4-D attention mask"):
+        AI.b200_attention_forward(None, q, k, v, additive.masked_fill(~padded, float("-inf")), scaling=0.2, is_causal=True)
     from transformers import AttentionInterface
 
     name = AI.register()
