@@ -270,6 +270,20 @@ int lv_patch_embed(const void* images, const void* W, const void* bias, const vo
                    void* out, void* ws, int64_t n, int64_t img, int64_t ps, int64_t C,
                    lv_stream_t stream);
 
+/* Cross-entropy over vocabulary CHUNKS, fused with the logit-masked LM head: replaces
+ * `compute_language_model_loss(labels, logits)` = vocab_parallel_cross_entropy(logits.float(), labels) on a
+ * materialised [M, vocab] tensor (long_vita_megatron/core/models/multimodal/gpt_vl_model.py:371-414; Megatron
+ * core_r0.7.0 tensor_parallel/cross_entropy.py, un-vendored).  The caller runs lv_gemm_bias_act per chunk of W rows.
+ * lv_ce_accumulate: logits bf16 [rows, cols] (row stride ld) = columns [col0, col0 + cols) of the full logits;
+ *   folds the chunk into run_max / run_sum (float [rows], initialise to -inf / 0) and writes tgt[r] = logit of
+ *   labels[r] when it falls inside the chunk.  After the last chunk: loss[r] = log(run_sum[r]) + run_max[r] - tgt[r].
+ * lv_ce_grad: dlogits[r, c] = bf16((exp(logits[r, c] - lse[r]) - [col0 + c == labels[r]]) * dloss[r]); rows with a
+ *   negative label produce zeros.  dlogits may alias logits. */
+int lv_ce_accumulate(const void* logits, int64_t ld, const int64_t* labels, float* run_max, float* run_sum, float* tgt,
+                     int64_t rows, int64_t cols, int64_t col0, lv_stream_t stream);
+int lv_ce_grad(const void* logits, int64_t ld, void* dlogits, int64_t ldd, const int64_t* labels, const float* lse,
+               const float* dloss, int64_t rows, int64_t cols, int64_t col0, lv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

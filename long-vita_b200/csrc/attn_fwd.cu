@@ -47,6 +47,7 @@ struct AttnKParams {
   int block_major; // 1: order work items (q-block, kv-head, head) - global longest-first; 0: (kv-head, q-block, head)
   int serpentine;  // 1: odd rounds sweep the item list backwards (default); LV_ATTN_SCHED=0 turns it off for A/B runs
   int poly_exp;    // 1: every 4th exponential of the softmax runs on the FMA pipe (polynomial), the rest on MUFU
+  int mufu_turns;  // 1: the two softmax warps of an SM sub-partition take turns on its MUFU unit (LV_ATTN_TURNS=0: off)
   float* lse;
 };
 
@@ -354,7 +355,8 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   uint64_t* p_full = s_full + 2;          // [2]
   uint64_t* o_full = p_full + 2;          // [2]
   uint64_t* p_q = o_full + 2;             // [2 tiles][4 quarters]  (QH only)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_q + 8);
+  uint64_t* tok = p_q + 8;                // [2 tiles][4 SM sub-partitions]: MUFU turn-taking, see the softmax warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -372,6 +374,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
       mbar_init(&o_full[i], 1);
     }
     for (int i = 0; i < 8; ++i) mbar_init(&p_q[i], 4);
+    for (int i = 0; i < 8; ++i) mbar_init(&tok[i], 1);
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -560,10 +563,23 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     const uint32_t tO = tmem_base + lane_base + (t == 0 ? Cfg::TM_O0 : Cfg::TM_O1);
     uint8_t* stage = sQ + t * Cfg::TILE_BYTES;
     uint32_t item_cnt = 0, scnt = 0, ocnt = 0;
+    // MUFU turn-taking.  The exponentials of one 128 x 128 score tile keep the MUFU unit of each SM sub-partition
+    // busy for ~1050 cycles - as long as the two MMAs (P.V of the other tile, Q.K^T of its next step) that must run
+    // meanwhile.  When the two softmax warps of a sub-partition (one per query tile) run their exp phases at the
+    // same time, both take twice as long and the tensor pipe then waits for both (ncu, round 2: tensor pipe 58 %, XU
+    // 58 %, softmax warps 28 % of their time waiting for S).  So the warps of a sub-partition take turns: tile 0's
+    // warp runs exp(j), then tile 1's warp exp(j), then tile 0's exp(j+1) ...; the load / max / store / hand-off
+    // parts of one warp overlap the exp phase of the other.  tok[t][quad] is arrived by the OTHER tile's warp when
+    // its exp phase ends; waits and arrivals are paired exactly (both sides know n[0], n[1] of the item).
+    uint64_t* tok_mine = &tok[t * 4 + quad];
+    uint64_t* tok_other = &tok[(1 - t) * 4 + quad];
+    uint32_t tok_cnt = 0;
+    const bool turns = p.mufu_turns != 0;
 
     for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
       const WorkItem w = decode_item(p, item);
       const int n = w.n[t];
+      const int n_other = w.n[1 - t];
       const long long qpos = w.qpos[t] + row;           // global position of this thread's query row
       float m_used = 0.f, l = 0.f;
       for (int j = 0; j < n; ++j) {
@@ -630,6 +646,15 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         // ---- P = exp2(S * scale_log2 - m), row sum, bf16 pack, store over S in TMEM ----
         const float neg_m = -m_used;
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        if (turns) {
+          // my turn on this sub-partition's MUFU?  tile 0 goes first in every step: it waits for tile 1's step j-1,
+          // tile 1 waits for tile 0's step j (only where the other tile has that step at all)
+          const bool need = (t == 0) ? (j >= 1 && j - 1 < n_other) : (j < n_other);
+          if (need) {
+            mbar_wait(tok_mine, tok_cnt & 1);
+            ++tok_cnt;
+          }
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
@@ -637,6 +662,13 @@ __global__ void __launch_bounds__(A_THREADS, 1)
             softmax_exp_chunk<true>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
           else
             softmax_exp_chunk<false>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
+          if (c == 3 && turns) {
+            // the exponentials of this step are issued: hand the MUFU turn over (tile 0 -> tile 1's step j,
+            // tile 1 -> tile 0's step j + 1) before the store / fence / hand-off tail of this step
+            const bool give = (t == 0) ? (j < n_other) : (j + 1 < n_other);
+            __syncwarp();
+            if (give && lane == 0) mbar_arrive(tok_other);
+          }
           tmem_st16(tS + c * 16, pk);
           if (QH) {
             tmem_wait_st();          // (also covers the lazy O rescale before the first quarter)
@@ -1165,6 +1197,11 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
   if (order_env >= 0 && a->causal) p.block_major = order_env;
   p.lse = a->lse;
   p.poly_exp = attn_poly_exp();
+  static const int turns_env = [] {
+    const char* e = getenv("LV_ATTN_TURNS");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  p.mufu_turns = turns_env;
   static const int serp = [] {
     const char* e = getenv("LV_ATTN_SCHED");
     return (e != nullptr && e[0] == '0') ? 0 : 1;

@@ -523,6 +523,88 @@ __global__ void __launch_bounds__(128) decode_merge_kernel(const __nv_bfloat16* 
   if (c == 0 && lse_out != nullptr) lse_out[kvh * G + g] = sum > 0.f ? m + __logf(sum) : -INFINITY;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Cross-entropy over the vocabulary in chunks, fused with the logit-masked LM head
+// (gpt_vl_model.py:371-414 computes `compute_language_model_loss(labels, logits)` =
+// vocab_parallel_cross_entropy(logits.float(), labels) on the full [M, vocab] logits).  The LM-head GEMM
+// produces bf16 logits of ONE vocabulary chunk [M, Vc]; `ce_accumulate_kernel` folds the chunk into running
+// per-row (max, sum-exp, target logit) in fp32 - the softmax statistics of the whole row without the row ever
+// existing - and `ce_grad_kernel` turns a recomputed chunk into d_logits = (softmax - onehot) * d_loss for the
+// backward GEMMs.  One CTA per row (grid-stride), two passes over the 2*Vc-byte row (the second from L1/L2).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(256) ce_accumulate_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld,
+                                                            const int64_t* __restrict__ labels, float* __restrict__ run_max,
+                                                            float* __restrict__ run_sum, float* __restrict__ tgt,
+                                                            int64_t rows, int cols, int64_t col0) {
+  __shared__ float red[8];
+  const int nvec = cols / 8;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const __nv_bfloat16* x = logits + row * ld;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < nvec; c += blockDim.x) {
+      float v[8];
+      unpack(ldg_vec(x + c * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx = fmaxf(mx, v[j]);
+    }
+    mx = block_reduce(mx, red, true);
+    const float m_old = run_max[row];
+    const float m_new = fmaxf(m_old, mx);
+    float sum = 0.f;
+    for (int c = threadIdx.x; c < nvec; c += blockDim.x) {
+      float v[8];
+      unpack(ldg_vec(x + c * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += __expf(v[j] - m_new);
+    }
+    sum = block_reduce(sum, red, false);
+    if (threadIdx.x == 0) {
+      const float l_old = run_sum[row];
+      run_sum[row] = (m_old == -INFINITY ? 0.f : l_old * __expf(m_old - m_new)) + sum;
+      run_max[row] = m_new;
+      const int64_t lab = labels[row] - col0;
+      if (lab >= 0 && lab < cols) tgt[row] = __bfloat162float(x[lab]);
+    }
+  }
+}
+
+// d_logits[row, c] = bf16( (exp(logit - lse) - [c == label]) * d_loss[row] ); rows whose label is `ignore` (< 0) get zeros.
+__global__ void __launch_bounds__(256) ce_grad_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld,
+                                                      __nv_bfloat16* __restrict__ dlogits, int64_t ldd,
+                                                      const int64_t* __restrict__ labels, const float* __restrict__ lse,
+                                                      const float* __restrict__ dloss, int64_t rows, int cols, int64_t col0) {
+  const int nvec = cols / 8;
+  const int64_t total = rows * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / nvec;
+    const int c = (int)(i - row * nvec);
+    float v[8];
+    unpack(ldg_stream(logits + row * ld + c * 8), v);
+    const int64_t lab = labels[row];
+    const float g = lab < 0 ? 0.f : dloss[row];
+    const float l = lse[row];
+    const int64_t hit = lab - col0 - (int64_t)c * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (__expf(v[j] - l) - (hit == j ? 1.f : 0.f)) * g;
+    stg_vec(dlogits + row * ldd + c * 8, pack(v));
+  }
+}
+
 }  // namespace lv
 
 using namespace lv;
@@ -778,6 +860,37 @@ int lv_swiglu_bwd(const void* gate_up, const void* dh, void* d_gate_up, int64_t 
   const int64_t total = rows * (inter / 8);
   swiglu_bwd_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(BF(gate_up), BF(dh), BFM(d_gate_up), rows, inter);
   LV_CHECK_LAUNCH("swiglu_bwd_kernel");
+  return LV_OK;
+}
+
+int lv_ce_accumulate(const void* logits, int64_t ld, const int64_t* labels, float* run_max, float* run_sum, float* tgt,
+                     int64_t rows, int64_t cols, int64_t col0, lv_stream_t stream) {
+  LV_CHECK_ARG(logits && labels && run_max && run_sum && tgt, "lv_ce_accumulate: null pointer");
+  LV_CHECK_ARG(cols > 0 && cols % 8 == 0 && ld % 8 == 0 && ld >= cols && cols < (1ll << 31), "lv_ce_accumulate: cols=%lld / ld=%lld must be multiples of 8", (long long)cols, (long long)ld);
+  LV_CHECK_ARG(aligned16(logits), "lv_ce_accumulate: logits must be 16-byte aligned");
+  if (rows == 0) return LV_OK;
+  LV_BIND_DEVICE(logits);
+  const int64_t cap = 8 * (int64_t)lv::sm_count();
+  ce_accumulate_kernel<<<(unsigned)(rows < cap ? rows : cap), 256, 0, (cudaStream_t)stream>>>(BF(logits), ld, labels, run_max, run_sum, tgt,
+                                                                                              rows, (int)cols, col0);
+  LV_CHECK_LAUNCH("ce_accumulate_kernel");
+  return LV_OK;
+}
+
+int lv_ce_grad(const void* logits, int64_t ld, void* dlogits, int64_t ldd, const int64_t* labels, const float* lse,
+               const float* dloss, int64_t rows, int64_t cols, int64_t col0, lv_stream_t stream) {
+  LV_CHECK_ARG(logits && dlogits && labels && lse && dloss, "lv_ce_grad: null pointer");
+  LV_CHECK_ARG(cols > 0 && cols % 8 == 0 && ld % 8 == 0 && ldd % 8 == 0 && ld >= cols && ldd >= cols && cols < (1ll << 31),
+               "lv_ce_grad: cols=%lld / ld=%lld / ldd=%lld must be multiples of 8", (long long)cols, (long long)ld, (long long)ldd);
+  LV_CHECK_ARG(aligned16(logits) && aligned16(dlogits), "lv_ce_grad: pointers must be 16-byte aligned");
+  if (rows == 0) return LV_OK;
+  LV_BIND_DEVICE(logits);
+  const int64_t total = rows * (cols / 8);
+  const int64_t cap = 16 * (int64_t)lv::sm_count();
+  const int64_t blocks = cdiv(total, 256);
+  ce_grad_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(BF(logits), ld, BFM(dlogits), ldd, labels, lse,
+                                                                                            dloss, rows, (int)cols, col0);
+  LV_CHECK_LAUNCH("ce_grad_kernel");
   return LV_OK;
 }
 

@@ -503,12 +503,17 @@ class LongVITAForCausalLM(_WeightHolderModule):
         hidden = outputs.last_hidden_state  # [1, s, H]
         # hidden_states[:, -num_logits_to_keep:, :] (modeling_long_vita.py:311); 0 keeps every row
         sel = hidden[:, -num_logits_to_keep:, :] if num_logits_to_keep else hidden
-        logits = ops.linear(sel.reshape(-1, sel.shape[-1]), self.lm_head).view(1, sel.shape[1], -1)
+        rows = sel.reshape(-1, sel.shape[-1])
+        logits = ops.linear(rows, self.lm_head).view(1, sel.shape[1], -1)
         loss = None
         if labels is not None:
-            # loss_function of transformers (shifted CE in fp32); host-side torch, off the hot path
-            lg = logits.float()[:, :-1].reshape(-1, logits.shape[-1])
-            loss = torch.nn.functional.cross_entropy(lg, labels[:, -logits.shape[1]:][:, 1:].reshape(-1), ignore_index=-100)
+            # transformers' loss_function (ForCausalLMLoss): labels shifted by one, mean of the per-token CE in fp32 over
+            # the labels != -100.  Per-token CE from the chunked LM-head + CE kernels (ops.lm_head_ce_fwd): same bf16
+            # logits, fp32 loss, and no fp32 copy of the [s, vocab] logits.
+            tgt = labels[:, -logits.shape[1]:][:, 1:].reshape(-1).to(rows.device)
+            per_tok, _ = ops.lm_head_ce_fwd(rows[:-1], self.lm_head, torch.where(tgt == -100, torch.full_like(tgt, -1), tgt))
+            n_valid = (tgt != -100).sum().clamp_min(1)
+            loss = per_tok.sum() / n_valid
         out = CausalLMOutput(loss=loss, logits=logits, past_key_values=outputs.past_key_values,
                              hidden_states=outputs.hidden_states)
         return out if (return_dict is None or return_dict) else out.to_tuple()

@@ -185,6 +185,28 @@ class B200GPTVLModel:
             h, _ = ops.rmsnorm(delta, self.final_layernorm, cfg.rms_norm_eps, residual=x)
         hidden_states = h.view(s, 1, -1)
 
+        # training tail, fused: masked row gather -> LM head -> per-token cross-entropy, chunked over the vocabulary so
+        # the [M, vocab] logits never exist.  Taken when nothing between the head and the loss needs
+        # the logits themselves (no multiplier / soft-capping; the NaN probe of :393 reads the loss instead).
+        if (labels is not None and logit_mask is not None and not self.output_multiplier_scale
+                and not self.output_logit_softcapping and getattr(self, "fused_loss", True)):
+            assert logit_mask.size(0) == 1
+            mask = logit_mask.to(hidden_states.device).to(torch.bool)
+            with torch.no_grad():
+                lab = torch.masked_select(labels.to(hidden_states.device), mask).reshape(1, -1)
+            if self.is_instruction_dataset:
+                # labels[:, 1:] against logits[:-1] (:386-388): drop the last selected row and the first label
+                keep = mask.clone()
+                last = mask.reshape(-1).nonzero().view(-1)[-1:]
+                keep.view(-1)[last] = False
+                mask, lab = keep, lab[:, 1:].contiguous()
+            loss = ops.masked_lm_head_ce(hidden_states, self.output_weight, mask, lab)
+            if loss.sum().isnan():
+                rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+                raise ValueError(f"Rank {rank}: found NaN in local forward logits calculation. "
+                                 f"Device: {loss.device}, node: {os.uname()[1]}")
+            return loss
+
         # output layer (ColumnParallelLinear with logit_mask, layers.py:402-409, 825-904)
         if logit_mask is not None:
             logits = ops.masked_linear(hidden_states, self.output_weight, logit_mask.to(hidden_states.device))

@@ -565,6 +565,127 @@ def masked_linear_autograd(h: torch.Tensor, weight: torch.Tensor, logit_mask: to
 
 
 # ------------------------------------------------------------------------------------------------
+# logit-masked LM head fused with the cross-entropy, chunked over the vocabulary
+# ------------------------------------------------------------------------------------------------
+def _ce_chunks(vocab: int, chunk: int):
+    chunk = max(8, (chunk // 8) * 8)
+    return [(v0, min(vocab, v0 + chunk)) for v0 in range(0, vocab, chunk)]
+
+
+def ce_accumulate(logits: torch.Tensor, labels: torch.Tensor, run_max: torch.Tensor, run_sum: torch.Tensor, tgt: torch.Tensor,
+                  col0: int) -> None:
+    """Fold one vocabulary chunk of bf16 logits [M, n] (columns col0 .. col0 + n of the full row) into the running
+    fp32 row statistics (in place): max, sum of exp(. - max), and the target logit where labels fall in the chunk."""
+    _need_cuda_bf16(logits)
+    M, n = logits.shape
+    _lib.check(_lib.lib().lv_ce_accumulate(logits.data_ptr(), logits.stride(0), labels.data_ptr(), run_max.data_ptr(),
+                                           run_sum.data_ptr(), tgt.data_ptr(), M, n, col0, _stream()), "lv_ce_accumulate")
+
+
+def ce_grad(logits: torch.Tensor, labels: torch.Tensor, lse: torch.Tensor, dloss: torch.Tensor, col0: int) -> torch.Tensor:
+    """In place: logits[M, n] (a vocabulary chunk) -> d_logits = (exp(logits - lse) - onehot) * dloss (bf16)."""
+    _need_cuda_bf16(logits)
+    M, n = logits.shape
+    _lib.check(_lib.lib().lv_ce_grad(logits.data_ptr(), logits.stride(0), logits.data_ptr(), logits.stride(0), labels.data_ptr(),
+                                     lse.data_ptr(), dloss.data_ptr(), M, n, col0, _stream()), "lv_ce_grad")
+    return logits
+
+
+def lm_head_ce_fwd(sel: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, vocab_chunk: int = 16384):
+    """Per-row cross-entropy of `sel @ weight.T` against `labels` without materialising the [M, vocab] logits:
+    for every chunk of `vocab_chunk` weight rows one GEMM into a [M, chunk] bf16 buffer + `lv_ce_accumulate`.
+    sel [M, c] bf16, weight [vocab, c] bf16 (vocab % 8 == 0), labels [M] int64 (negative = ignored -> loss 0).
+    Returns (loss [M] fp32, lse [M] fp32).  Same arithmetic as the reference: bf16 logits (the output dtype of its
+    ColumnParallelLinear), then the loss in fp32 (gpt_vl_model.py:371-414 -> logits.float())."""
+    M, c = sel.shape
+    V = weight.shape[0]
+    dev = sel.device
+    run_max = torch.full((M,), float("-inf"), dtype=torch.float32, device=dev)
+    run_sum = torch.zeros((M,), dtype=torch.float32, device=dev)
+    tgt = torch.zeros((M,), dtype=torch.float32, device=dev)
+    if M == 0:
+        return run_sum, run_sum.clone()
+    labels = labels.contiguous()
+    chunks = _ce_chunks(V, vocab_chunk)
+    buf = torch.empty((M, chunks[0][1] - chunks[0][0]), dtype=torch.bfloat16, device=dev)
+    for v0, v1 in chunks:
+        lg = linear(sel, weight[v0:v1], out=buf[:, : v1 - v0])
+        ce_accumulate(lg, labels, run_max, run_sum, tgt, v0)
+    lse = torch.log(run_sum) + run_max
+    loss = torch.where(labels >= 0, lse - tgt, torch.zeros_like(lse))
+    return loss, lse
+
+
+def lm_head_ce_bwd(sel: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, lse: torch.Tensor, dloss: torch.Tensor,
+                   need_dsel: bool = True, need_dw: bool = False, vocab_chunk: int = 16384):
+    """Backward of lm_head_ce_fwd, chunk by chunk: the chunk's logits are recomputed (one GEMM), turned into
+    d_logits = (softmax - onehot) * dloss in place (`lv_ce_grad`), and contracted by the same tcgen05 GEMM:
+    d_sel += d_logits @ W[chunk] (fp32 accumulation across chunks), dW[chunk] = d_logits^T @ sel
+    (layers.py:443-456, 512-520).  Returns (d_sel [M, c] bf16 or None, dW [vocab, c] bf16 or None)."""
+    M, c = sel.shape
+    V = weight.shape[0]
+    dev = sel.device
+    dsel = torch.zeros((M, c), dtype=torch.float32, device=dev) if need_dsel else None
+    dw = torch.empty((V, c), dtype=torch.bfloat16, device=dev) if need_dw else None
+    if M == 0:
+        if dw is not None:
+            dw.zero_()
+        return (None if dsel is None else dsel.to(torch.bfloat16)), dw
+    labels = labels.contiguous()
+    dloss = dloss.contiguous().float()
+    chunks = _ce_chunks(V, vocab_chunk)
+    buf = torch.empty((M, chunks[0][1] - chunks[0][0]), dtype=torch.bfloat16, device=dev)
+    mp = (M + 7) // 8 * 8
+    if need_dw:
+        st = torch.zeros((c, mp), dtype=torch.bfloat16, device=dev)        # sel^T, contraction dim padded to 8
+        st[:, :M] = sel.t()
+    for v0, v1 in chunks:
+        n = v1 - v0
+        lg = ce_grad(linear(sel, weight[v0:v1], out=buf[:, :n]), labels, lse, dloss, v0)
+        if need_dsel:
+            wt = weight[v0:v1].t().contiguous()                             # [c, n] = the [N, K] operand of d_logits @ W
+            dsel += linear(lg, wt).float()
+        if need_dw:
+            gt = torch.zeros((n, mp), dtype=torch.bfloat16, device=dev)
+            gt[:, :M] = lg.t()
+            linear(gt, st, out=dw[v0:v1])
+    return (None if dsel is None else dsel.to(torch.bfloat16)), dw
+
+
+class _MaskedLMHeadCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, weight, logit_mask, labels, vocab_chunk):
+        s, b, c = h.shape
+        if b != 1:
+            raise NotImplementedError("masked_lm_head_ce: micro-batch 1")
+        idx = logit_mask.reshape(-1).nonzero().view(-1)
+        sel = row_gather(h.reshape(s, c), idx)
+        loss, lse = lm_head_ce_fwd(sel, weight, labels.reshape(-1), vocab_chunk)
+        ctx.save_for_backward(sel, weight, idx, labels.reshape(-1), lse)
+        ctx.s, ctx.vocab_chunk = s, vocab_chunk
+        return loss.view(1, -1)
+
+    @staticmethod
+    def backward(ctx, dloss):
+        sel, weight, idx, labels, lse = ctx.saved_tensors
+        dsel, dw = lm_head_ce_bwd(sel, weight, labels, lse, dloss.reshape(-1), ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                  ctx.vocab_chunk)
+        gh = None
+        if dsel is not None:
+            gh = row_scatter_zero(dsel, idx, ctx.s).view(ctx.s, 1, -1)
+        return gh, dw, None, None, None
+
+
+def masked_lm_head_ce(h: torch.Tensor, weight: torch.Tensor, logit_mask: torch.Tensor, labels: torch.Tensor,
+                      vocab_chunk: int = 16384) -> torch.Tensor:
+    """GPTVLModel's training tail in one differentiable op (gpt_vl_model.py:325-339 masked_select of the hidden rows,
+    :339 output_layer, :379-382 masked_select of the labels done by the caller, :412 per-token loss): h [s, 1, c],
+    weight [vocab, c], logit_mask [1, s] bool, labels [1, M] (the M selected label ids) -> loss [1, M] fp32.  The
+    [M, vocab] logits are never materialised (1M tokens x 152 064 would be 318 GB in bf16)."""
+    return _MaskedLMHeadCEFn.apply(h, weight, logit_mask, labels, vocab_chunk)
+
+
+# ------------------------------------------------------------------------------------------------
 # differentiable building blocks of the decoder layer (training through the `--spec` layer, SURVEY.md 8f-1)
 # ------------------------------------------------------------------------------------------------
 def rmsnorm_bwd(x: torch.Tensor, weight: torch.Tensor, dy: torch.Tensor, eps: float = 1e-6,

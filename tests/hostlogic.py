@@ -139,7 +139,31 @@ def _row_scatter_zero(x, idx, n_rows_out):
     return out
 
 
+def _ce_accumulate(logits, labels, run_max, run_sum, tgt, col0):
+    x = logits.float()
+    m_new = torch.maximum(run_max, x.max(dim=1).values)
+    run_sum.copy_(torch.where(torch.isinf(run_max), torch.zeros_like(run_sum), run_sum * torch.exp(run_max - m_new))
+                  + torch.exp(x - m_new[:, None]).sum(dim=1))
+    run_max.copy_(m_new)
+    lab = labels - col0
+    hit = (lab >= 0) & (lab < x.shape[1])
+    tgt[hit] = x[hit.nonzero().view(-1), lab[hit]]
+
+
+def _ce_grad(logits, labels, lse, dloss, col0):
+    x = logits.float()
+    p = torch.exp(x - lse[:, None])
+    lab = labels - col0
+    hit = (lab >= 0) & (lab < x.shape[1])
+    p[hit.nonzero().view(-1), lab[hit]] -= 1.0
+    g = torch.where(labels < 0, torch.zeros_like(dloss), dloss)
+    logits.copy_(_bf(p * g[:, None]))
+    return logits
+
+
 SUBSTITUTES = {
+    "ce_accumulate": _ce_accumulate,
+    "ce_grad": _ce_grad,
     "attention_fwd": _attention_fwd,
     "attention_bwd": _attention_bwd,
     "decode_merge": _decode_merge,

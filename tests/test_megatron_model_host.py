@@ -142,7 +142,13 @@ def test_labels_give_per_token_loss_and_inference_params_override(tiny, model):
     assert logits.shape == (1, 20, cfg.vocab_size)
     assert loss.shape == (1, 20) and loss.dtype == torch.float32
     ref = torch.nn.functional.cross_entropy(logits[0].float(), labels[0, 280:], reduction="none")
-    assert torch.allclose(loss[0], ref, rtol=0, atol=0)
+    # fused LM head + chunked cross-entropy: the same bf16 logits, the fp32 log-sum-exp summed chunk by chunk
+    assert torch.allclose(loss[0], ref, rtol=1e-6, atol=1e-5)
+    model.fused_loss = False                                            # the un-fused tail (logits materialised) is exact
+    with oracle_ops():
+        loss_u = model(ids, pos, None, labels=labels, external_inputs={"images": images, "indices": idx}, logit_mask=mask)
+    model.fused_loss = True
+    assert torch.allclose(loss_u[0], ref, rtol=0, atol=0)
     full = _oracle_logits(cfg, hf, ids, images, idx, slice(280, 300))
     assert rel_fro(logits[0], full) < 1.5e-2
 
@@ -478,6 +484,12 @@ def test_forward_glue_equals_the_references_own_gptvl_forward(tiny, model):
             for kw in cases:
                 want = ref_forward(me, ids, pos, None, **kw)
                 got = model(ids, pos, None, **kw)
+                if "labels" in kw:
+                    # fused LM head + chunked cross-entropy (8f-3): same bf16 logits, fp32 log-sum-exp summed per chunk
+                    assert got.shape == want.shape and torch.allclose(got, want, rtol=1e-6, atol=1e-5), sorted(kw)
+                    model.fused_loss = False        # the un-fused tail reproduces the reference's glue bit for bit
+                    got = model(ids, pos, None, **kw)
+                    model.fused_loss = True
                 assert got.shape == want.shape and torch.equal(got, want), sorted(kw)
     finally:
         dist.destroy_process_group()
@@ -637,3 +649,34 @@ def test_spec_layer_trains_gradients_match_oracle_autograd(tiny):
         want = ref_mc["decoder.layers.0." + name]
         assert prm.grad is not None and prm.grad.shape == want.shape, name
         assert rel_fro(prm.grad, want) < 3e-2, (name, rel_fro(prm.grad, want))
+
+
+def test_fused_masked_lm_head_cross_entropy_host_logic():
+    """SURVEY.md 8f-3 host logic on CPU: the chunked LM-head + cross-entropy composition (chunk loop, running softmax
+    statistics, gradient chunks, scatter of dX) equals cross_entropy over the materialised logits and its autograd."""
+    from long_vita_b200 import ops
+
+    g = torch.Generator().manual_seed(12)
+    s, c, V = 40, 64, 200          # 200 = 3 chunks of 64 + a ragged 8
+    h = (torch.randn(s, 1, c, generator=g)).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(V, c, generator=g) * 0.2).to(torch.bfloat16).requires_grad_(True)
+    mask = torch.rand(1, s, generator=g) < 0.4
+    M = int(mask.sum())
+    labels = torch.randint(0, V, (1, M), generator=g)
+    up = torch.randn(1, M, generator=g)
+    with oracle_ops():
+        loss = ops.masked_lm_head_ce(h, w, mask, labels, vocab_chunk=64)
+        loss.backward(up)
+    hf, wf = h.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    logits = (hf[mask[0]][:, 0] @ wf.t()).to(torch.bfloat16).float()      # bf16 logits, fp32 loss (the reference's dtypes)
+    ref = torch.nn.functional.cross_entropy(logits, labels[0], reduction="none")
+    assert loss.shape == (1, M) and loss.dtype == torch.float32
+    assert torch.allclose(loss[0], ref, rtol=1e-5, atol=1e-5)
+    ref32 = torch.nn.functional.cross_entropy(hf[mask[0]][:, 0] @ wf.t(), labels[0], reduction="none")
+    ref32.backward(up[0])
+    assert rel_fro(h.grad, hf.grad) < 1e-2 and rel_fro(w.grad, wf.grad) < 1e-2
+    assert torch.equal(h.grad[~mask[0]], torch.zeros_like(h.grad[~mask[0]]))           # masked_scatter into zeros
+    # ignored rows (negative label): zero loss, zero gradient
+    with oracle_ops():
+        l2, lse = ops.lm_head_ce_fwd(h.detach()[mask[0]][:, 0], w.detach(), torch.cat([labels[0, :-1], torch.tensor([-1])]), 64)
+    assert float(l2[-1]) == 0.0 and torch.allclose(l2[:-1], ref[:-1], rtol=1e-5, atol=1e-5)
