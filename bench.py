@@ -368,6 +368,7 @@ def main():
         from long_vita_b200 import cp as cpmod
 
         runner = cpmod.ContextParallelRunner(model, dist.group.WORLD)
+        runner.check_faults = False     # the per-forward fault check synchronises the stream; checked once after the timed region
     else:
         runner = None
 
@@ -447,6 +448,8 @@ def main():
         step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    if runner is not None and runner.ctx is not None:
+        runner.ctx.check()      # raises if any in-kernel wait on a peer GPU timed out during the run
 
     if rank != 0:
         if world > 1:

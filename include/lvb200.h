@@ -141,9 +141,14 @@ typedef struct lv_cp_params {
   void* v_full;
   void* blk_flags;           /* uint32 [S/128], zero-initialised once; private to the kernel (it counts
                               * staged 32-token units: 4 * (epoch + 1) when block b of this epoch is whole) */
+  void* fault;               /* uint32, zero-initialised once (local device memory): sticky fault word */
 } lv_cp_params;
 
 int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv_stream_t stream);
+/* Every in-kernel wait on another GPU's progress is bounded (LV_CP_TIMEOUT_MS, default 120 000): on expiry the kernel
+ * sets the sticky fault word, stops waiting and finishes with undefined output instead of hanging the node.
+ * lv_cp_check_fault synchronises the stream and returns LV_ESTATE (+ lv_last_error text) once the word is set. */
+int lv_cp_check_fault(const void* fault, lv_stream_t stream);
 
 /* Peer-mappable device memory (cudaMalloc + CUDA IPC).  The 64-byte handle is exchanged by the
  * host (torch.distributed) and opened on the other ranks of the node. */

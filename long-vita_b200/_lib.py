@@ -50,7 +50,7 @@ class CpParams(C.Structure):
     _fields_ = [
         ("rank", c_i32), ("cp", c_i32), ("seq_total", c_i64), ("epoch", C.c_uint32), ("peer_tok_stride", c_i64),
         ("peer_kv", c_ptr * 8), ("peer_ready", c_ptr * 8), ("my_ready", c_ptr),
-        ("k_full", c_ptr), ("v_full", c_ptr), ("blk_flags", c_ptr),
+        ("k_full", c_ptr), ("v_full", c_ptr), ("blk_flags", c_ptr), ("fault", c_ptr),
     ]
 
 
@@ -62,6 +62,7 @@ SIGNATURES = {
     "lv_attn_fwd": (c_i32, [C.POINTER(AttnParams), c_ptr]),
     "lv_attn_bwd": (c_i32, [C.POINTER(AttnBwdParams), c_ptr]),
     "lv_attn_cp_fwd": (c_i32, [C.POINTER(AttnParams), C.POINTER(CpParams), c_ptr]),
+    "lv_cp_check_fault": (c_i32, [c_ptr, c_ptr]),
     "lv_ipc_alloc": (c_i32, [c_i64, C.POINTER(c_ptr)]),
     "lv_ipc_free": (c_i32, [c_ptr]),
     "lv_ipc_get_handle": (c_i32, [c_ptr, c_ptr]),

@@ -246,6 +246,7 @@ class CPContext(CPBackwardMixin):
         self.k_full = torch.empty((seq_total, hkv * d), dtype=torch.bfloat16, device=device)
         self.v_full = torch.empty((seq_total, hkv * d), dtype=torch.bfloat16, device=device)
         self.blk_flags = torch.zeros(seq_total // 128, dtype=torch.int32, device=device)
+        self.fault = torch.zeros(1, dtype=torch.int32, device=device)     # sticky: set by a kernel whose peer wait timed out
         dist.barrier(group=group)
 
     def close(self) -> None:
@@ -264,7 +265,13 @@ class CPContext(CPBackwardMixin):
         dist.barrier(group=self.group)
         self._check(self.lib.lv_ipc_free(self.base), "lv_ipc_free")
         self.base = None
-        self.k_full = self.v_full = self.blk_flags = None
+        self.k_full = self.v_full = self.blk_flags = self.fault = None
+
+    def check(self) -> None:
+        """Raise (LV_ESTATE) if any attention kernel of this context gave up waiting for a peer rank: every in-kernel
+        wait on another GPU is bounded (LV_CP_TIMEOUT_MS), so a dead or diverged peer costs an error here instead of a
+        hung node.  Synchronises the current stream - call it where the host reads a result anyway."""
+        self._check(self.lib.lv_cp_check_fault(self.fault.data_ptr(), torch.cuda.current_stream().cuda_stream), "lv_cp_check_fault")
 
     def qkv_buffer(self) -> torch.Tensor:
         """The peer-mapped [T, row] buffer the NEXT attention call reads: the fused QKV GEMM writes
@@ -325,6 +332,7 @@ class CPContext(CPBackwardMixin):
             cpp.peer_ready[p] = self.peer_base[p] + 2 * self.qkv_bytes
         cpp.my_ready = self.ready_ptr
         cpp.k_full, cpp.v_full, cpp.blk_flags = self.k_full.data_ptr(), self.v_full.data_ptr(), self.blk_flags.data_ptr()
+        cpp.fault = self.fault.data_ptr()
         from . import ops
 
         ev0 = ops._TIMER.start() if ops._TIMER is not None else None
@@ -348,6 +356,7 @@ class ContextParallelRunner:
         self.cp = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.ctx: Optional[CPContext] = None
+        self.check_faults = True   # synchronise + read the exchange's fault word at the end of every forward
         self.cache = None          # this rank's K/V cache shard after forward(..., use_cache=True)
         self.total_len = 0         # tokens in the whole (sharded) cache
 
@@ -401,6 +410,8 @@ class ContextParallelRunner:
         logits = ops.linear(h[row : row + 1], self.model.lm_head).view(1, 1, -1)
         if gather_logits:
             dist.broadcast(logits, src=dist.get_global_rank(self.group, 0), group=self.group)
+        if self.check_faults:
+            ctx.check()        # a peer that never published its K/V shows up here as an error, not as a hang
         return logits
 
     # -- incremental decoding over the sharded cache (SURVEY.md 8f-2 under context parallelism) --------------

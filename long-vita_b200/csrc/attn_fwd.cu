@@ -69,6 +69,41 @@ struct CpKParams {
   __nv_bfloat16* k_full;             // staging [S, hkv*d]
   __nv_bfloat16* v_full;
   uint32_t* blk_flags;               // [S / 128]
+  uint32_t* fault;                   // sticky fault word (0 = healthy); set when a peer wait times out
+  unsigned long long timeout_ns;     // bound of one wait on another GPU's progress
+};
+
+// Waits on ANOTHER GPU's progress are bounded: a rank whose peer died (or never launched this layer) would otherwise
+// spin forever and, because every other rank waits for it in turn, hang the whole node with no message.  After
+// `timeout_ns` the waiter records a code in the sticky fault word and STOPS WAITING - the kernel finishes (its output
+// is garbage), later waits of this and of the following launches return at once, and the host turns the word into
+// LV_ESTATE at its next check (lv_cp_check_fault).  The clock is read every 1024 polls only.
+constexpr uint32_t CP_FAULT_READY = 1u, CP_FAULT_BLOCK = 2u, CP_FAULT_EXIT = 4u;
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+struct PeerWait {
+  unsigned long long t0 = 0;
+  uint32_t polls = 0;
+  // true: give up (fault already set by someone, or this wait timed out and sets it)
+  __device__ __forceinline__ bool expired(const CpKParams& c, uint32_t code) {
+    if ((++polls & 1023u) != 0) return false;
+    if (*reinterpret_cast<volatile uint32_t*>(c.fault) != 0) return true;
+    const unsigned long long now = global_ns();
+    if (t0 == 0) {
+      t0 = now;
+      return false;
+    }
+    if (now - t0 > c.timeout_ns) {
+      atomicOr(c.fault, code);
+      return true;
+    }
+    return false;
+  }
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -177,8 +212,10 @@ __device__ __forceinline__ void cp_copier(const CpKParams& cpp, int warp, int la
           if (lane == 0)
             {
               [[maybe_unused]] uint32_t spins = 0;
+              PeerWait pw;
               while (ld_acquire_sys(cpp.my_ready + owner) < cpp.epoch1) {
                 LV_SPIN_GUARD(spins, "peer ready word", cpp.my_ready + owner, cpp.epoch1)
+                if (pw.expired(cpp, CP_FAULT_READY)) break;
               }
             }
           __syncwarp();
@@ -241,8 +278,10 @@ __device__ __forceinline__ void cp_copier(const CpKParams& cpp, int warp, int la
         if (lane < cpp.cp && lane != cpp.rank)
         {
           [[maybe_unused]] uint32_t spins = 0;
+          PeerWait pw;
           while (ld_acquire_sys(cpp.my_ready + lane) < cpp.epoch1) {
             LV_SPIN_GUARD(spins, "peer epoch word (exit)", cpp.my_ready + lane, cpp.epoch1)
+            if (pw.expired(cpp, CP_FAULT_EXIT)) break;
           }
         }
         __syncwarp();
@@ -412,8 +451,10 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           if (CP && j >= ready_upto) {
             {
               [[maybe_unused]] uint32_t spins = 0;
+              PeerWait pw;
               while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1 * CP_SUB) {
                 LV_SPIN_GUARD(spins, "staged block flag", cpp.blk_flags + j, cpp.epoch1 * CP_SUB)
+                if (pw.expired(cpp, CP_FAULT_BLOCK)) break;
               }
             }
             ready_upto = j + 1;
@@ -875,8 +916,10 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           if (CP && j >= ready_upto) {
             {
               [[maybe_unused]] uint32_t spins = 0;
+              PeerWait pw;
               while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1 * CP_SUB) {
                 LV_SPIN_GUARD(spins, "staged block flag", cpp.blk_flags + j, cpp.epoch1 * CP_SUB)
+                if (pw.expired(cpp, CP_FAULT_BLOCK)) break;
               }
             }
             ready_upto = j + 1;
@@ -1320,6 +1363,14 @@ extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv
   k.k_full = reinterpret_cast<__nv_bfloat16*>(c->k_full);
   k.v_full = reinterpret_cast<__nv_bfloat16*>(c->v_full);
   k.blk_flags = reinterpret_cast<uint32_t*>(c->blk_flags);
+  LV_CHECK_ARG(c->fault != nullptr, "lv_attn_cp_fwd: null fault word");
+  k.fault = reinterpret_cast<uint32_t*>(c->fault);
+  static const unsigned long long timeout_ms = [] {
+    const char* e = getenv("LV_CP_TIMEOUT_MS");
+    const long long v = e ? atoll(e) : 0;
+    return (unsigned long long)(v > 0 ? v : 120000);      // 2 minutes: far beyond any rank skew of a healthy job
+  }();
+  k.timeout_ns = timeout_ms * 1000000ull;
   if (attn_version() == 2) return launch_attn<128, false, true, 2>(a, &k, (cudaStream_t)stream);
   if (attn_version() == 3) return launch_attn<128, true, true, 1>(a, &k, (cudaStream_t)stream);
   return launch_attn<128, false, true, 1>(a, &k, (cudaStream_t)stream);
@@ -1353,6 +1404,22 @@ extern "C" int lv_ipc_open_handle(const void* handle64, void** ptr) {
   LV_CHECK_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
   return LV_OK;
 }
+// Read (and keep) the sticky fault word of a context-parallel context: LV_OK when healthy, LV_ESTATE with a message
+// naming what timed out otherwise.  Synchronises `stream` (the word is written by kernels on it).
+extern "C" int lv_cp_check_fault(const void* fault, lv_stream_t stream) {
+  LV_CHECK_ARG(fault != nullptr, "lv_cp_check_fault: null pointer");
+  LV_BIND_DEVICE(fault);
+  uint32_t w = 0;
+  LV_CHECK_CUDA(cudaMemcpyAsync(&w, fault, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  LV_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (w == 0) return LV_OK;
+  lv::set_error("context-parallel exchange timed out (fault word 0x%x:%s%s%s): a peer rank did not publish its K/V rows "
+                "for this layer in time - it died, hung, or is not running the same sequence of attention calls",
+                w, (w & CP_FAULT_READY) ? " peer-ready" : "", (w & CP_FAULT_BLOCK) ? " staged-block" : "",
+                (w & CP_FAULT_EXIT) ? " exit-handshake" : "");
+  return LV_ESTATE;
+}
+
 extern "C" int lv_ipc_close_handle(void* ptr) {
   if (ptr) LV_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
   return LV_OK;

@@ -185,3 +185,42 @@ def test_context_parallel_sharded_cache_decode(lib_built, world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     mp.spawn(_decode_worker, args=(world, _free_port()), nprocs=world, join=True)
+
+
+def _fault_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LV_CP_TIMEOUT_MS="1500")
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import time
+
+        from long_vita_b200 import cp as CP
+
+        hq, hkv, d = 10, 2, 128
+        S = 2 * world * 128
+        ctx = CP.CPContext(dist.group.WORLD, S, hq, hkv, d, dev)
+        ctx.qkv_buffer().normal_()
+        out = ctx.attention()            # healthy epoch 0 on both ranks
+        ctx.check()
+        if rank == 0:
+            ctx.qkv_buffer().normal_()
+            t0 = time.time()
+            ctx.attention()              # rank 1 never runs this epoch: the peer wait must time out, not hang
+            with pytest.raises(RuntimeError, match="timed out"):
+                ctx.check()
+            assert time.time() - t0 < 30.0
+            with pytest.raises(RuntimeError, match="code -4"):     # LV_ESTATE, sticky
+                ctx.check()
+        else:
+            time.sleep(6.0)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_a_missing_peer_times_out_with_an_error_instead_of_hanging(lib_built):
+    """Bounded in-kernel waits (LV_CP_TIMEOUT_MS): a rank whose peer never publishes its K/V rows gets LV_ESTATE."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_fault_worker, args=(2, _free_port()), nprocs=2, join=True)

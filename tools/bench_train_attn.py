@@ -24,6 +24,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seq", type=int, default=131072)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--cp", type=int, default=0, help="context-parallel group size (default: all ranks); ranks / cp = "
+                    "data-parallel replicas, each with its own sequence (BASELINE config 5: 8 ranks, --cp 4 -> DP2 x CP4)")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -35,14 +37,24 @@ def main():
     from long_vita_b200 import ops
 
     hq, hkv, d = 40, 8, 128
-    S = a.seq // (2 * max(world, 1) * 128) * (2 * max(world, 1) * 128)
-    T = S // max(world, 1)
+    cp = a.cp if a.cp else max(world, 1)
+    assert world % cp == 0
+    dp = world // cp
+    group = None
+    if world > 1:
+        # consecutive ranks form a CP group (Megatron's rank order: CP varies fastest inside a DP replica)
+        for r0 in range(0, world, cp):
+            g_ = dist.new_group(list(range(r0, r0 + cp)))
+            if r0 <= rank < r0 + cp:
+                group = g_
+    S = a.seq // (2 * cp * 128) * (2 * cp * 128)
+    T = S // cp
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     q = torch.randn(T, hq, d, device=dev, generator=g).to(torch.bfloat16).requires_grad_(True)
     k = torch.randn(T, hkv, d, device=dev, generator=g).to(torch.bfloat16).requires_grad_(True)
     v = torch.randn(T, hkv, d, device=dev, generator=g).to(torch.bfloat16).requires_grad_(True)
     d_out = torch.randn(T, hq * d, device=dev, generator=g).to(torch.bfloat16)
-    ctx = CP.CPContext(dist.group.WORLD, S, hq, hkv, d, dev, fused_qkv=False) if world > 1 else None
+    ctx = CP.CPContext(group, S, hq, hkv, d, dev, fused_qkv=False) if cp > 1 else None
 
     def step():
         for t in (q, k, v):
@@ -75,10 +87,12 @@ def main():
         f_flops = 4.0 * hq * d * (S * (S + 1) / 2)
         fwd_ms, bwd_ms = float(t[0]), float(t[1])
         print(json.dumps({"what": "attention fwd+bwd, one layer, causal 40:8x128", "seq": S, "n_gpus": world,
+                          "parallelism": f"dp{dp} x cp{cp}", "sequences_per_step": dp,
                           "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
-                          "fwd_tflops_per_gpu": f_flops / fwd_ms / 1e9 / world,
-                          "bwd_tflops_per_gpu": 2.5 * f_flops / bwd_ms / 1e9 / world,
-                          "step_ms_48_layers": 48 * (fwd_ms + bwd_ms)}))
+                          "fwd_tflops_per_gpu": f_flops / fwd_ms / 1e9 / cp,
+                          "bwd_tflops_per_gpu": 2.5 * f_flops / bwd_ms / 1e9 / cp,
+                          "step_ms_48_layers": 48 * (fwd_ms + bwd_ms),
+                          "tokens_per_s_attention_only_48_layers": dp * S / (48 * (fwd_ms + bwd_ms) / 1e3)}))
     if world > 1:
         dist.destroy_process_group()
 
