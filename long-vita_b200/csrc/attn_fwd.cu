@@ -369,9 +369,9 @@ __device__ __forceinline__ WorkItem decode_item(const AttnKParams& p, int item) 
   return w;
 }
 
-// QH (quarter hand-off): the softmax warps publish P in four 32-key quarters and the issuer starts the
-// P.V k-steps of a quarter as soon as it lands, so the PV MMA overlaps the exp phase of the same tile.
-template <int D, bool QH, bool CP>
+// POLY: every 4th exponential on the FMA pipe (ex2_poly).  TURNS: MUFU turn-taking of the two softmax warps of an
+// SM sub-partition (see the softmax section).  Both are compile-time so the per-step loop carries no flag tests.
+template <int D, bool CP, bool POLY, bool TURNS>
 __global__ void __launch_bounds__(A_THREADS, 1)
     attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -393,8 +393,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   uint64_t* s_full = bars + 4 + 4 * NS;   // [2]
   uint64_t* p_full = s_full + 2;          // [2]
   uint64_t* o_full = p_full + 2;          // [2]
-  uint64_t* p_q = o_full + 2;             // [2 tiles][4 quarters]  (QH only)
-  uint64_t* tok = p_q + 8;                // [2 tiles][4 SM sub-partitions]: MUFU turn-taking, see the softmax warps
+  uint64_t* tok = o_full + 2;             // [2 tiles][4 SM sub-partitions]: MUFU turn-taking, see the softmax warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 8);
 
   const int warp = threadIdx.x >> 5;
@@ -412,7 +411,6 @@ __global__ void __launch_bounds__(A_THREADS, 1)
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&p_q[i], 4);
     for (int i = 0; i < 8; ++i) mbar_init(&tok[i], 1);
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
@@ -518,10 +516,6 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         const bool leader = elect_one();
 #pragma unroll
         for (int kk = 0; kk < A_BN / 16; ++kk) {
-          if (QH && (kk & 1) == 0) {
-            mbar_wait(&p_q[t * 4 + kk / 2], (pcnt[t] - 1) & 1);   // pcnt[t] was advanced by the caller
-            tc_fence_after();
-          }
           // A: P_t rows in TMEM, 16 bf16 (= 8 columns) per k-step.  B: V tile, MN-major: 16 key rows
           // (2 KB) per k-step, the second 64 head-dim columns live one 16 KB box further.
           if (leader) umma_ts(tO[t], tS[t] + kk * 8, vd + (uint64_t)(kk * 128), idesc_pv, (accumulate || kk != 0) ? 1u : 0u);
@@ -559,7 +553,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
                 mbar_wait(&v_full[vc % NS], (vc / NS) & 1);
                 ++vcnt_wait;
               }
-              if (!QH) mbar_wait(&p_full[1], pcnt[1] & 1);
+              mbar_wait(&p_full[1], pcnt[1] & 1);
               ++pcnt[1];
               tc_fence_after();
               issue_pv(1, vc % NS, j - 1 > 0);
@@ -583,7 +577,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
               mbar_wait(&v_full[vc % NS], (vc / NS) & 1);
               ++vcnt_wait;
             }
-            if (!QH) mbar_wait(&p_full[0], pcnt[0] & 1);
+            mbar_wait(&p_full[0], pcnt[0] & 1);
             ++pcnt[0];
             tc_fence_after();
             issue_pv(0, vc % NS, j > 0);
@@ -604,71 +598,87 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     const uint32_t tO = tmem_base + lane_base + (t == 0 ? Cfg::TM_O0 : Cfg::TM_O1);
     uint8_t* stage = sQ + t * Cfg::TILE_BYTES;
     uint32_t item_cnt = 0, scnt = 0, ocnt = 0;
-    // MUFU turn-taking.  The exponentials of one 128 x 128 score tile keep the MUFU unit of each SM sub-partition
-    // busy for ~1050 cycles - as long as the two MMAs (P.V of the other tile, Q.K^T of its next step) that must run
-    // meanwhile.  When the two softmax warps of a sub-partition (one per query tile) run their exp phases at the
-    // same time, both take twice as long and the tensor pipe then waits for both (ncu, round 2: tensor pipe 58 %, XU
-    // 58 %, softmax warps 28 % of their time waiting for S).  So the warps of a sub-partition take turns: tile 0's
-    // warp runs exp(j), then tile 1's warp exp(j), then tile 0's exp(j+1) ...; the load / max / store / hand-off
-    // parts of one warp overlap the exp phase of the other.  tok[t][quad] is arrived by the OTHER tile's warp when
-    // its exp phase ends; waits and arrivals are paired exactly (both sides know n[0], n[1] of the item).
-    uint64_t* tok_mine = &tok[t * 4 + quad];
-    uint64_t* tok_other = &tok[(1 - t) * 4 + quad];
+    // Everything the per-step loop touches is resolved ONCE here: 32-bit shared-window addresses of its barriers
+    // (a generic pointer costs an S2UR + uniform ALU chain per use), the scale, and per item the first step that
+    // needs a mask.  The ncu source view of round 2 showed ~900 of the ~3800 cycles of a (2 x 128 rows) x 128 keys
+    // step going to such scalar set-up on the softmax warps' critical path (profiles/README.md).
+    const uint32_t a_sfull = smem_u32(&s_full[t]), a_pfull = smem_u32(&p_full[t]), a_ofull = smem_u32(&o_full[t]);
+    const uint32_t a_qfull = smem_u32(&q_full[t]);
+    // MUFU turn-taking (TURNS): the exponentials of one 128 x 128 score tile keep the MUFU unit of an SM sub-partition
+    // busy for ~1050 cycles.  The two softmax warps of a sub-partition (one per query tile) take turns on it - tile
+    // 0's warp runs exp(j), then tile 1's exp(j), then tile 0's exp(j+1) ... - so that the load / max / store /
+    // hand-off parts of one warp overlap the exp phase of the other instead of both exp phases colliding.
+    // tok[t][quad] is arrived by the OTHER tile's warp when its exp phase ends; waits and arrivals are paired exactly
+    // (both sides know n[0], n[1] of the item).
+    const uint32_t a_tok_mine = smem_u32(&tok[t * 4 + quad]), a_tok_other = smem_u32(&tok[(1 - t) * 4 + quad]);
     uint32_t tok_cnt = 0;
-    const bool turns = p.mufu_turns != 0;
+    const float scale_log2 = p.scale_log2;
+    const int n_kv_tiles = (p.sk + A_BN - 1) / A_BN;
+    const int j_ragged = (p.sk % A_BN) ? n_kv_tiles - 1 : 0x7fffffff;
 
     for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
       const WorkItem w = decode_item(p, item);
       const int n = w.n[t];
       const int n_other = w.n[1 - t];
       const long long qpos = w.qpos[t] + row;           // global position of this thread's query row
+      // first key tile that needs a mask: the diagonal ones (kv_pos0 + 128 j + 127 > position of the tile's row 0)
+      // and the ragged last one
+      int j_mask = j_ragged;
+      if (p.causal) {
+        const long long dd = w.qpos[t] - p.kv_pos0 - (A_BN - 1);
+        const long long jd = dd < 0 ? 0 : dd / A_BN + 1;
+        if (jd < j_mask) j_mask = (int)jd;
+      }
       float m_used = 0.f, l = 0.f;
       for (int j = 0; j < n; ++j) {
-        mbar_wait(&s_full[t], scnt & 1);
+        mbar_wait_a(a_sfull, scnt & 1);
         ++scnt;
         tc_fence_after();
-        uint32_t s[4][32];
-        tmem_ld32(tS + 0, s[0]);
-        tmem_ld32(tS + 32, s[1]);
-        tmem_ld32(tS + 64, s[2]);
-        tmem_ld32(tS + 96, s[3]);
+        uint32_t s[128];
+        tmem_ld128(tS, s);
         tmem_wait_ld();
 
         // ---- mask (only diagonal tiles and the ragged last key tile) ----
-        const long long kidx0 = (long long)j * A_BN;
-        const bool ragged = kidx0 + A_BN > p.sk;
-        const bool diag = p.causal && (p.kv_pos0 + kidx0 + A_BN - 1 > w.qpos[t]);
-        if (ragged || diag) {
+        int live = 4;      // 32-column chunks with at least one visible key for some row of this warp (warp-uniform)
+        if (j >= j_mask) {
+          const long long kidx0 = (long long)j * A_BN;
           long long lim = p.sk - kidx0;                               // first invalid column (ragged)
+          long long lim_warp = lim;                                   // the same bound for the warp's LAST row
           if (p.causal) {
             const long long c = qpos - p.kv_pos0 - kidx0 + 1;         // first masked column (causal)
             if (c < lim) lim = c;
+            const long long cw = c + (31 - lane);
+            if (cw < lim_warp) lim_warp = cw;
           }
+          const int ilim = lim < 0 ? 0 : (lim > A_BN ? A_BN : (int)lim);
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= lim) s[c][i] = 0xff800000u;  // -inf
+          for (int i = 0; i < 128; ++i)
+            if (i >= ilim) s[i] = 0xff800000u;  // -inf
+          // chunks beyond the warp's last visible column hold only masked scores: their exponentials are skipped
+          // (P = 0).  The ragged last key tile of the ViT (1025 = 8 x 128 + 1 keys) costs 1 chunk instead of 4.
+          const int lw = __shfl_sync(0xffffffffu, lim_warp < 0 ? 0 : (lim_warp > A_BN ? A_BN : (int)lim_warp), 0);
+          live = (lw + 31) >> 5;
         }
 
-        // ---- row max ----
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        // ---- row max: 8 independent chains ----
+        float mx[8];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          mx0 = fmax3(mx0, __uint_as_float(s[0][i]), __uint_as_float(s[0][i + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(s[1][i]), __uint_as_float(s[1][i + 1]));
-          mx2 = fmax3(mx2, __uint_as_float(s[2][i]), __uint_as_float(s[2][i + 1]));
-          mx3 = fmax3(mx3, __uint_as_float(s[3][i]), __uint_as_float(s[3][i + 1]));
+        for (int c = 0; c < 8; ++c) mx[c] = fmax3(__uint_as_float(s[c * 16]), __uint_as_float(s[c * 16 + 1]), __uint_as_float(s[c * 16 + 2]));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+#pragma unroll
+          for (int i = 3; i < 15; i += 2) mx[c] = fmax3(mx[c], __uint_as_float(s[c * 16 + i]), __uint_as_float(s[c * 16 + i + 1]));
+          mx[c] = fmaxf(mx[c], __uint_as_float(s[c * 16 + 15]));
         }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+        const float mx_all = fmax3(fmax3(mx[0], mx[1], mx[2]), fmax3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])) * scale_log2;
 
         // ---- lazy rescale ----
         if (j == 0) {
-          m_used = (mx == -INFINITY) ? 0.f : mx;
+          m_used = (mx_all == -INFINITY) ? 0.f : mx_all;
         } else {
-          const bool grow = mx > m_used + 8.f;
+          const bool grow = mx_all > m_used + 8.f;
           if (__any_sync(0xffffffffu, grow)) {
-            const float m_new = fmaxf(m_used, mx);
+            const float m_new = fmaxf(m_used, mx_all);
             const float alpha = ex2(m_used - m_new);
             m_used = m_new;
             l *= alpha;
@@ -687,54 +697,52 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         // ---- P = exp2(S * scale_log2 - m), row sum, bf16 pack, store over S in TMEM ----
         const float neg_m = -m_used;
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-        if (turns) {
+        if (TURNS) {
           // my turn on this sub-partition's MUFU?  tile 0 goes first in every step: it waits for tile 1's step j-1,
           // tile 1 waits for tile 0's step j (only where the other tile has that step at all)
           const bool need = (t == 0) ? (j >= 1 && j - 1 < n_other) : (j < n_other);
           if (need) {
-            mbar_wait(tok_mine, tok_cnt & 1);
+            mbar_wait_a(a_tok_mine, tok_cnt & 1);
             ++tok_cnt;
           }
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-          if (p.poly_exp)
-            softmax_exp_chunk<true>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
-          else
-            softmax_exp_chunk<false>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
-          if (c == 3 && turns) {
+        for (int h = 0; h < 2; ++h) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (2 * h + c < live) {
+              softmax_exp_chunk<POLY>(reinterpret_cast<const uint32_t(&)[32]>(s[(2 * h + c) * 32]), scale_log2, neg_m, l0, l1, l2, l3,
+                                      reinterpret_cast<uint32_t(&)[16]>(pk[c * 16]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[c * 16 + i] = 0u;
+            }
+          }
+          if (h == 1 && TURNS) {
             // the exponentials of this step are issued: hand the MUFU turn over (tile 0 -> tile 1's step j,
             // tile 1 -> tile 0's step j + 1) before the store / fence / hand-off tail of this step
             const bool give = (t == 0) ? (j < n_other) : (j + 1 < n_other);
             __syncwarp();
-            if (give && lane == 0) mbar_arrive(tok_other);
+            if (give && lane == 0) mbar_arrive_a(a_tok_other);
           }
-          tmem_st16(tS + c * 16, pk);
-          if (QH) {
-            tmem_wait_st();          // (also covers the lazy O rescale before the first quarter)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_q[t * 4 + c]);
-          }
+          tmem_st32(tS + h * 32, pk);
         }
         l += (l0 + l1) + (l2 + l3);
-        if (!QH) {
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[t]);
-        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(a_pfull);
       }
 
       // ---------------- epilogue: O / l -> bf16 -> smem (swizzled) -> TMA store; LSE ----------------
       const float inv_l = (n > 0 && l > 0.f) ? 1.f / l : 0.f;
       if (n > 0) {
-        mbar_wait(&o_full[t], ocnt & 1);
+        mbar_wait_a(a_ofull, ocnt & 1);
         ++ocnt;
         tc_fence_after();
       } else {
-        mbar_wait(&q_full[t], item_cnt & 1);   // the Q load into the staging tile must have landed
+        mbar_wait_a(a_qfull, item_cnt & 1);   // the Q load into the staging tile must have landed
       }
 #pragma unroll 1
       for (int c = 0; c < D / 32; ++c) {
@@ -1194,8 +1202,8 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int D, bool QH, bool CP, int VER>
-static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_t s) {
+template <int D, bool CP, int VER, bool POLY = false, bool TURNS = true>
+static int launch_attn_t(const lv_attn_params* a, const CpKParams* cp, cudaStream_t s) {
   using Cfg = AttnCfg<D>;
   CUtensorMap tmQ, tmK, tmV, tmO;
   const uint32_t box[4] = {64, 128, 1, 1};
@@ -1239,12 +1247,8 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
   }();
   if (order_env >= 0 && a->causal) p.block_major = order_env;
   p.lse = a->lse;
-  p.poly_exp = attn_poly_exp();
-  static const int turns_env = [] {
-    const char* e = getenv("LV_ATTN_TURNS");
-    return (e != nullptr && e[0] == '0') ? 0 : 1;
-  }();
-  p.mufu_turns = turns_env;
+  p.poly_exp = attn_poly_exp();      // read by the v2 kernel only (v1: template parameter)
+  p.mufu_turns = TURNS ? 1 : 0;
   static const int serp = [] {
     const char* e = getenv("LV_ATTN_SCHED");
     return (e != nullptr && e[0] == '0') ? 0 : 1;
@@ -1256,7 +1260,7 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
     if constexpr (VER == 2) {
       LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<D, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     } else {
-      LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, QH, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
+      LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, CP, POLY, TURNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     }
     attr_once.done(attr_dev);
   }
@@ -1270,21 +1274,47 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
   if constexpr (VER == 2)
     attn_fwd2_kernel<D, CP><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p, cpp);
   else
-    attn_fwd_kernel<D, QH, CP><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p, cpp);
+    attn_fwd_kernel<D, CP, POLY, TURNS><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p, cpp);
   LV_CHECK_LAUNCH("attn_fwd_kernel");
   return LV_OK;
+}
+
+// LV_ATTN_TURNS=0 / 1 forces the MUFU turn-taking of the softmax warps off / on (default: on at head_dim 128, where
+// the step is latency-bound; off at head_dim 64, where the MUFU is the bottleneck outright and two warps per
+// sub-partition use it better than one).  LV_ATTN_POLY=1: every 4th exponential on the FMA pipe.
+static int attn_turns_env() {
+  static const int v = [] {
+    const char* e = getenv("LV_ATTN_TURNS");
+    return (e != nullptr && (e[0] == '0' || e[0] == '1')) ? (e[0] - '0') : -1;
+  }();
+  return v;
+}
+
+template <int D, bool CP, int VER>
+static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_t s) {
+  if constexpr (VER == 2) {
+    return launch_attn_t<D, CP, 2>(a, cp, s);
+  } else {
+    const bool turns = attn_turns_env() >= 0 ? attn_turns_env() == 1 : (D == 128);
+    if constexpr (CP) {     // context-parallel launches: the default pair only (fewer instantiations of the big kernel)
+      return turns ? launch_attn_t<D, CP, 1, false, true>(a, cp, s) : launch_attn_t<D, CP, 1, false, false>(a, cp, s);
+    } else {
+      const bool poly = attn_poly_exp() != 0;
+      if (poly) return turns ? launch_attn_t<D, CP, 1, true, true>(a, cp, s) : launch_attn_t<D, CP, 1, true, false>(a, cp, s);
+      return turns ? launch_attn_t<D, CP, 1, false, true>(a, cp, s) : launch_attn_t<D, CP, 1, false, false>(a, cp, s);
+    }
+  }
 }
 
 }  // namespace lv
 
 using namespace lv;
 
-// LV_ATTN_VERSION: 1 = single-S-buffer kernel (default), 2 = double-buffered-S kernel (correct, slower),
-// 3 = kernel 1 with the quarter-wise P hand-off.
+// LV_ATTN_VERSION: 1 = single-S-buffer kernel (default), 2 = double-buffered-S kernel (correct, slower).
 static int attn_version() {
   static const int v = [] {
     const char* e = getenv("LV_ATTN_VERSION");
-    return (e != nullptr && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 1;
+    return (e != nullptr && e[0] >= '1' && e[0] <= '2') ? (e[0] - '0') : 1;
   }();
   return v;
 }
@@ -1315,15 +1345,11 @@ extern "C" int lv_attn_fwd(const lv_attn_params* a, lv_stream_t stream) {
   // P is bf16 like V: tcgen05 kind::f16 faults on an fp16 A operand against a bf16 B operand
   // (measured on B200), so the fp16-P instantiation is never launched.
   if (attn_version() == 2) {
-    if (a->d == 128) return launch_attn<128, false, false, 2>(a, nullptr, s);
-    return launch_attn<64, false, false, 2>(a, nullptr, s);
+    if (a->d == 128) return launch_attn<128, false, 2>(a, nullptr, s);
+    return launch_attn<64, false, 2>(a, nullptr, s);
   }
-  if (attn_version() == 3) {
-    if (a->d == 128) return launch_attn<128, true, false, 1>(a, nullptr, s);
-    return launch_attn<64, true, false, 1>(a, nullptr, s);
-  }
-  if (a->d == 128) return launch_attn<128, false, false, 1>(a, nullptr, s);
-  return launch_attn<64, false, false, 1>(a, nullptr, s);
+  if (a->d == 128) return launch_attn<128, false, 1>(a, nullptr, s);
+  return launch_attn<64, false, 1>(a, nullptr, s);
 }
 
 extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv_stream_t stream) {
@@ -1371,9 +1397,8 @@ extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv
     return (unsigned long long)(v > 0 ? v : 120000);      // 2 minutes: far beyond any rank skew of a healthy job
   }();
   k.timeout_ns = timeout_ms * 1000000ull;
-  if (attn_version() == 2) return launch_attn<128, false, true, 2>(a, &k, (cudaStream_t)stream);
-  if (attn_version() == 3) return launch_attn<128, true, true, 1>(a, &k, (cudaStream_t)stream);
-  return launch_attn<128, false, true, 1>(a, &k, (cudaStream_t)stream);
+  if (attn_version() == 2) return launch_attn<128, true, 2>(a, &k, (cudaStream_t)stream);
+  return launch_attn<128, true, 1>(a, &k, (cudaStream_t)stream);
 }
 
 // Peer-mappable ("symmetric") allocations for the context-parallel K/V exchange: plain cudaMalloc
