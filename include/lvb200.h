@@ -289,6 +289,18 @@ int lv_ce_accumulate(const void* logits, int64_t ld, const int64_t* labels, floa
 int lv_ce_grad(const void* logits, int64_t ld, void* dlogits, int64_t ldd, const int64_t* labels, const float* lse,
                const float* dloss, int64_t rows, int64_t cols, int64_t col0, lv_stream_t stream);
 
+/* Frame preprocessing: decoded uint8 RGB frames [n, H, W, 3] -> bf16 [n, 3, S, S], bit-identical to
+ * ImageProcessor.process_images (long_vita/data/processor/image_processor.py:183-223: expand2square with the mean
+ * colour, PIL BICUBIC resize to S x S, * 1/255, (x - mean) / std in float32, channel-first) followed by .to(bfloat16).
+ * win_min / win_cnt int32 [S] and coeff int32 [S, ksize] are Pillow's resampling windows and 22-bit fixed-point
+ * weights for max(H, W) -> S pixels (device memory; computed once per geometry by the host, see
+ * long_vita_b200/preprocess.py); background int32[3], mean / std float[3] are HOST arrays; ws is device workspace of
+ * lv_frame_preprocess_ws_bytes() bytes (the uint8 intermediate of the horizontal pass). */
+int64_t lv_frame_preprocess_ws_bytes(int64_t n_frames, int64_t H, int64_t W, int64_t S);
+int lv_frame_preprocess(const void* frames, void* out, void* ws, const int32_t* win_min, const int32_t* win_cnt,
+                        const int32_t* coeff, int64_t ksize, int64_t n_frames, int64_t H, int64_t W, int64_t S,
+                        const int32_t* background, const float* mean, const float* std, lv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,42 @@ struct CpKParams {
   uint32_t* blk_flags;               // [S / 128]
   uint32_t* fault;                   // sticky fault word (0 = healthy); set when a peer wait times out
   unsigned long long timeout_ns;     // bound of one wait on another GPU's progress
+  unsigned long long order;          // chunk visiting order of this rank, 4 bits per entry (2 cp entries): its own two
+                                     // chunks first, then the peers' by ring distance (rank - 1, rank - 2, ...)
+  int tiles_per_chunk;               // chunk / 128
+};
+
+// Visiting order of the key tiles under context parallelism.  Online softmax does not care in which order the key
+// tiles of a query row arrive, so every rank starts on the K/V rows it owns (no waiting at all) and then walks the
+// peers in ring order - rank r reads from r-1 first, r-2 next ... - which staggers the ranks over the NVSwitch ports
+// instead of all of them pulling chunk 0 from rank 0 at once (the "ring" schedule of TE / ring-flash-attn, SURVEY.md
+// 8e).  The two query tiles of a work item share the K/V tiles, and tile t must take part in a PREFIX of the steps
+// (steps j < n[t]): the tiles [0, lo) that both see come first, then [lo, hi), each range in chunk-priority order.
+struct KvWalk {
+  int lo, hi, a, b, li, g, gend;
+  __device__ __forceinline__ void begin(int n0, int n1) {
+    lo = min(n0, n1);
+    hi = max(n0, n1);
+    a = 0;
+    b = lo;
+    li = -1;
+    g = gend = 0;
+  }
+  // global index of the next key tile (call exactly hi times per item)
+  __device__ __forceinline__ int next(const CpKParams& c) {
+    for (;;) {
+      if (g < gend) return g++;
+      if (++li >= 2 * c.cp) {       // first range done: the tiles only the longer query tile sees
+        a = lo;
+        b = hi;
+        li = -1;
+        continue;
+      }
+      const int ch = (int)((c.order >> (4 * li)) & 15ull);
+      g = max(a, ch * c.tiles_per_chunk);
+      gend = min(b, (ch + 1) * c.tiles_per_chunk);
+    }
+  }
 };
 
 // Waits on ANOTHER GPU's progress are bounded: a rank whose peer died (or never launched this layer) would otherwise
@@ -203,8 +239,22 @@ __device__ __forceinline__ void cp_copier(const CpKParams& cpp, int warp, int la
       const int vec_per_half = cpp.kv_row_elems / 8;
       const int n_units = cpp.nblk_needed * CP_SUB;
       for (int u = cw; u < n_units; u += ncw) {
-        const int b = u / CP_SUB;
-        const int tok0 = b * A_BN + (u - b * CP_SUB) * CP_UNIT_ROWS;
+        // the i-th block in this rank's chunk-priority order (own chunks, then peers by ring distance): the order in
+        // which the query tiles consume them (KvWalk)
+        int b = u / CP_SUB;
+        {
+          int i = b;
+          for (int li = 0; li < 2 * cpp.cp; ++li) {
+            const int ch = (int)((cpp.order >> (4 * li)) & 15ull);
+            const int cnt = min(max(cpp.nblk_needed - ch * cpp.tiles_per_chunk, 0), cpp.tiles_per_chunk);
+            if (i < cnt) {
+              b = ch * cpp.tiles_per_chunk + i;
+              break;
+            }
+            i -= cnt;
+          }
+        }
+        const int tok0 = b * A_BN + (u % CP_SUB) * CP_UNIT_ROWS;
         const int chunk = tok0 / cpp.chunk;
         const int owner = chunk < cpp.cp ? chunk : 2 * cpp.cp - 1 - chunk;
         const int lrow0 = (chunk < cpp.cp ? 0 : cpp.chunk) + (tok0 - chunk * cpp.chunk);
@@ -434,10 +484,11 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (lane == 0) {
       uint32_t item_cnt = 0, kcnt = 0, vcnt = 0;
-      int ready_upto = 0;   // CP: key blocks [0, ready_upto) are known to be staged
+      KvWalk walk;
       for (int round = 0, item; (item = sched_item(round, p.n_items, p.serpentine)) >= 0; ++round, ++item_cnt) {
         const WorkItem w = decode_item(p, item);
         const int nmax = max(w.n[0], w.n[1]);
+        if (CP) walk.begin(w.n[0], w.n[1]);
         for (int t = 0; t < 2; ++t) {
           mbar_wait(&q_empty[t], (item_cnt & 1) ^ 1);
           mbar_arrive_expect_tx(&q_full[t], Cfg::TILE_BYTES);
@@ -446,16 +497,19 @@ __global__ void __launch_bounds__(A_THREADS, 1)
                         kEvictFirst);
         }
         for (int j = 0; j < nmax; ++j) {
-          if (CP && j >= ready_upto) {
+          int g = j;            // global key tile visited in step j
+          if (CP) {
+            g = walk.next(cpp);
+            // staged by the copier warps of this GPU (any CTA)?  One L2 poll per tile; the K / V rings keep the
+            // producer a step ahead of the tensor pipe, so the poll latency is off the critical path.
             {
               [[maybe_unused]] uint32_t spins = 0;
               PeerWait pw;
-              while (ld_acquire_gpu(cpp.blk_flags + j) < cpp.epoch1 * CP_SUB) {
-                LV_SPIN_GUARD(spins, "staged block flag", cpp.blk_flags + j, cpp.epoch1 * CP_SUB)
+              while (ld_acquire_gpu(cpp.blk_flags + g) < cpp.epoch1 * CP_SUB) {
+                LV_SPIN_GUARD(spins, "staged block flag", cpp.blk_flags + g, cpp.epoch1 * CP_SUB)
                 if (pw.expired(cpp, CP_FAULT_BLOCK)) break;
               }
             }
-            ready_upto = j + 1;
             fence_proxy_async_all();   // copier warps wrote the staging rows through the generic proxy
           }
           {
@@ -463,7 +517,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
             mbar_wait(&k_empty[st], ((kcnt / NS) & 1) ^ 1);
             mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
             for (int bx = 0; bx < Cfg::BOXES; ++bx)
-              tma_load_4d(sK + st * Cfg::TILE_BYTES + bx * 16384, &tmK, &k_full[st], bx * 64, j * A_BN, w.kvh, w.b,
+              tma_load_4d(sK + st * Cfg::TILE_BYTES + bx * 16384, &tmK, &k_full[st], bx * 64, g * A_BN, w.kvh, w.b,
                           kEvictLast);
             ++kcnt;
           }
@@ -472,7 +526,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
             mbar_wait(&v_empty[st], ((vcnt / NS) & 1) ^ 1);
             mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
             for (int bx = 0; bx < Cfg::BOXES; ++bx)
-              tma_load_4d(sV + st * Cfg::TILE_BYTES + bx * 16384, &tmV, &v_full[st], bx * 64, j * A_BN, w.kvh, w.b,
+              tma_load_4d(sV + st * Cfg::TILE_BYTES + bx * 16384, &tmV, &v_full[st], bx * 64, g * A_BN, w.kvh, w.b,
                           kEvictLast);
             ++vcnt;
           }
@@ -621,8 +675,10 @@ __global__ void __launch_bounds__(A_THREADS, 1)
       const int n = w.n[t];
       const int n_other = w.n[1 - t];
       const long long qpos = w.qpos[t] + row;           // global position of this thread's query row
-      // first key tile that needs a mask: the diagonal ones (kv_pos0 + 128 j + 127 > position of the tile's row 0)
-      // and the ragged last one
+      // first key tile (GLOBAL index) that needs a mask: the diagonal ones (kv_pos0 + 128 g + 127 > position of the
+      // tile's row 0) and the ragged last one
+      KvWalk walk;
+      if (CP) walk.begin(w.n[0], w.n[1]);
       int j_mask = j_ragged;
       if (p.causal) {
         const long long dd = w.qpos[t] - p.kv_pos0 - (A_BN - 1);
@@ -631,6 +687,8 @@ __global__ void __launch_bounds__(A_THREADS, 1)
       }
       float m_used = 0.f, l = 0.f;
       for (int j = 0; j < n; ++j) {
+        int g = j;         // global key tile of this step (context parallelism visits them out of order)
+        if (CP) g = walk.next(cpp);
         mbar_wait_a(a_sfull, scnt & 1);
         ++scnt;
         tc_fence_after();
@@ -640,8 +698,8 @@ __global__ void __launch_bounds__(A_THREADS, 1)
 
         // ---- mask (only diagonal tiles and the ragged last key tile) ----
         int live = 4;      // 32-column chunks with at least one visible key for some row of this warp (warp-uniform)
-        if (j >= j_mask) {
-          const long long kidx0 = (long long)j * A_BN;
+        if (g >= j_mask) {
+          const long long kidx0 = (long long)g * A_BN;
           long long lim = p.sk - kidx0;                               // first invalid column (ragged)
           long long lim_warp = lim;                                   // the same bound for the warp's LAST row
           if (p.causal) {
@@ -1397,6 +1455,20 @@ extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv
     return (unsigned long long)(v > 0 ? v : 120000);      // 2 minutes: far beyond any rank skew of a healthy job
   }();
   k.timeout_ns = timeout_ms * 1000000ull;
+  // chunk visiting order: own chunks, then the peers' by ring distance (LV_CP_ORDER=0: plain global order, for A/B runs)
+  k.tiles_per_chunk = (int)(chunk / A_BN);
+  static const int ring_order = [] {
+    const char* e = getenv("LV_CP_ORDER");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  k.order = 0;
+  for (int i = 0; i < c->cp; ++i) {
+    const int peer = ring_order ? (c->rank - i + c->cp) % c->cp : i;
+    const unsigned long long first = ring_order ? (unsigned long long)peer : (unsigned long long)(2 * i);
+    const unsigned long long second = ring_order ? (unsigned long long)(2 * c->cp - 1 - peer) : (unsigned long long)(2 * i + 1);
+    k.order |= first << (4 * (2 * i));
+    k.order |= second << (4 * (2 * i + 1));
+  }
   if (attn_version() == 2) return launch_attn<128, true, 2>(a, &k, (cudaStream_t)stream);
   return launch_attn<128, true, 1>(a, &k, (cudaStream_t)stream);
 }

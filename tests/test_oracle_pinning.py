@@ -397,3 +397,43 @@ def test_live_megatron_local_rmsnorm_matches_oracle_bit_exact():
     me = types.SimpleNamespace(eps=1e-6, weight=w)
     me._norm = lambda t: m["_norm"](me, t)
     assert torch.equal(m["forward"](me, x), O.rmsnorm(x, w, 1e-6))
+
+
+# ---- frame preprocessing: Pillow's fixed-point bicubic resize + normalisation ----
+def test_frame_preprocessing_oracle_matches_the_references_own_process_images_fixture():
+    """tests/golden/ref_preprocess.pt = outputs of the reference's own ImageProcessor.process_images
+    (image_processor.py:183-223, run from /root/reference with Pillow) on seeded frames: wide, tall, square,
+    down- and up-scaled.  The numpy restatement of Pillow's 8-bit resample must reproduce them bit for bit."""
+    import numpy as np
+
+    from oracle import preprocess as P
+
+    g = torch.load(os.path.join(GOLD, "ref_preprocess.pt"))
+    for frames, want in zip(g["frames"], g["out"]):
+        got = P.process_frames(list(frames.numpy()), image_size=g["image_size"])
+        assert got.dtype == np.float32 and np.array_equal(got, want.numpy()), frames.shape
+
+
+def test_frame_preprocessing_oracle_matches_the_reference_live_at_448():
+    if not ref_loader.available():
+        pytest.skip("/root/reference is not mounted")
+    import sys
+
+    import numpy as np
+
+    sys.path.insert(0, GOLD)
+    from make_golden import reference_process_images
+
+    from oracle import preprocess as P
+
+    rng = np.random.default_rng(7)
+    for h, w in [(360, 640), (500, 333), (448, 448), (100, 100), (448, 600)]:
+        f = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+        assert np.array_equal(P.process_frames(list(f)), reference_process_images(f, 448).numpy()), (h, w)
+    # the product's host-side coefficient tables (long_vita_b200/preprocess.py) are the oracle's
+    from long_vita_b200 import preprocess as PP
+
+    for a in (1920, 640, 500, 448, 100):
+        xm, cn, kk = P.resample_coeffs(a, 448)
+        x2, c2, r2, _ = PP.resample_table(a, 448)
+        assert np.array_equal(xm, np.array(x2)) and np.array_equal(cn, np.array(c2)) and np.array_equal(kk, np.array(r2))
