@@ -343,7 +343,11 @@ struct AttnCfg {
   static constexpr int KV_STAGES = (D == 128) ? 2 : 4;
   static constexpr int TILE_BYTES = 128 * D * 2;           // one 128-row tile of Q / K / V
   static constexpr int BOXES = D / 64;                     // 64-column (128-byte) TMA boxes per row
-  static constexpr int SMEM_Q = 2 * TILE_BYTES;
+  // Q tiles of two work items in flight when they fit (head_dim 64: 4 x 16 KB): the next item's Q lands while this
+  // one computes, and its first Q.K^T does not wait for this item's epilogue.  Short items - the ViT's 9 key tiles per
+  // (frame, head, 256 rows) - otherwise pay an exposed TMA round trip (~1.5 us) per item.
+  static constexpr int QBUF = (D == 64) ? 2 : 1;
+  static constexpr int SMEM_Q = QBUF * 2 * TILE_BYTES;
   static constexpr int SMEM_K = KV_STAGES * TILE_BYTES;
   static constexpr int SMEM_V = KV_STAGES * TILE_BYTES;
   static constexpr int SMEM_BAR = 512;
@@ -434,16 +438,18 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   uint8_t* sK = sQ + Cfg::SMEM_Q;
   uint8_t* sV = sK + Cfg::SMEM_K;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Cfg::SMEM_V);
-  uint64_t* q_full = bars;            // [2]
-  uint64_t* q_empty = bars + 2;       // [2]
-  uint64_t* k_full = bars + 4;        // [NS]
-  uint64_t* k_empty = bars + 4 + NS;  // [NS]
-  uint64_t* v_full = bars + 4 + 2 * NS;
-  uint64_t* v_empty = bars + 4 + 3 * NS;
-  uint64_t* s_full = bars + 4 + 4 * NS;   // [2]
+  constexpr int QB = Cfg::QBUF;
+  uint64_t* q_full = bars;            // [QB][2]
+  uint64_t* q_empty = bars + 4;       // [QB][2]
+  uint64_t* k_full = bars + 8;        // [NS]
+  uint64_t* k_empty = bars + 8 + NS;  // [NS]
+  uint64_t* v_full = bars + 8 + 2 * NS;
+  uint64_t* v_empty = bars + 8 + 3 * NS;
+  uint64_t* s_full = bars + 8 + 4 * NS;   // [2]
   uint64_t* p_full = s_full + 2;          // [2]
   uint64_t* o_full = p_full + 2;          // [2]
-  uint64_t* tok = o_full + 2;             // [2 tiles][4 SM sub-partitions]: MUFU turn-taking, see the softmax warps
+  uint64_t* o_free = o_full + 2;          // [2]: the epilogue has read O_t out of TMEM (the next item's first P.V overwrites it)
+  uint64_t* tok = o_free + 2;             // [2 tiles][4 SM sub-partitions]: MUFU turn-taking, see the softmax warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 8);
 
   const int warp = threadIdx.x >> 5;
@@ -454,12 +460,15 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmO);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 4);
     }
     for (int i = 0; i < 8; ++i) mbar_init(&tok[i], 1);
     for (int i = 0; i < NS; ++i) {
@@ -489,14 +498,9 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         const WorkItem w = decode_item(p, item);
         const int nmax = max(w.n[0], w.n[1]);
         if (CP) walk.begin(w.n[0], w.n[1]);
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&q_empty[t], (item_cnt & 1) ^ 1);
-          mbar_arrive_expect_tx(&q_full[t], Cfg::TILE_BYTES);
-          for (int bx = 0; bx < Cfg::BOXES; ++bx)
-            tma_load_4d(sQ + t * Cfg::TILE_BYTES + bx * 16384, &tmQ, &q_full[t], bx * 64, w.row0[t], w.h, w.b,
-                        kEvictFirst);
-        }
-        for (int j = 0; j < nmax; ++j) {
+        const int qb = (int)(item_cnt % QB);
+        const uint32_t qpar = (item_cnt / QB) & 1;
+        auto load_kv = [&](int j) {
           int g = j;            // global key tile visited in step j
           if (CP) {
             g = walk.next(cpp);
@@ -530,7 +534,19 @@ __global__ void __launch_bounds__(A_THREADS, 1)
                           kEvictLast);
             ++vcnt;
           }
+        };
+        // With a single Q buffer the Q loads of this item wait for the previous item's epilogue; its first key tiles
+        // do not (their ring slots free up as the previous item's last MMAs retire), so they are requested first.
+        const int pre = (QB == 1) ? min(NS, nmax) : 0;
+        for (int j = 0; j < pre; ++j) load_kv(j);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&q_empty[qb * 2 + t], qpar ^ 1);
+          mbar_arrive_expect_tx(&q_full[qb * 2 + t], Cfg::TILE_BYTES);
+          for (int bx = 0; bx < Cfg::BOXES; ++bx)
+            tma_load_4d(sQ + (qb * 2 + t) * Cfg::TILE_BYTES + bx * 16384, &tmQ, &q_full[qb * 2 + t], bx * 64, w.row0[t], w.h, w.b,
+                        kEvictFirst);
         }
+        for (int j = pre; j < nmax; ++j) load_kv(j);
       }
     }
   } else if (warp == 1) {
@@ -550,7 +566,8 @@ __global__ void __launch_bounds__(A_THREADS, 1)
       uint32_t pcnt[2] = {0, 0};
 
       // tiles are 1024-byte aligned, so stepping a descriptor is a plain add on its 14-bit address field
-      const uint64_t qdesc[2] = {make_smem_desc(smem_u32(sQ), 16, 1024), make_smem_desc(smem_u32(sQ + Cfg::TILE_BYTES), 16, 1024)};
+      const uint64_t qdesc0 = make_smem_desc(smem_u32(sQ), 16, 1024);
+      uint64_t qdesc[2] = {qdesc0, qdesc0};
       const uint64_t kdesc0 = make_smem_desc(smem_u32(sK), 16, 1024);
       const uint64_t vdesc0 = make_smem_desc(smem_u32(sV), 16384, 1024);
       auto issue_qk = [&](int t, int kst) {
@@ -585,9 +602,14 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         const WorkItem w = decode_item(p, item);
         const int n0 = w.n[0], n1 = w.n[1];
         const int nmax = max(n0, n1);
-        mbar_wait(&q_full[0], item_cnt & 1);
-        mbar_wait(&q_full[1], item_cnt & 1);
+        const int qb = (int)(item_cnt % QB);
+        const uint32_t qpar = (item_cnt / QB) & 1;
+        qdesc[0] = qdesc0 + (uint64_t)(((qb * 2 + 0) * Cfg::TILE_BYTES) >> 4);
+        qdesc[1] = qdesc0 + (uint64_t)(((qb * 2 + 1) * Cfg::TILE_BYTES) >> 4);
+        mbar_wait(&q_full[qb * 2 + 0], qpar);
+        mbar_wait(&q_full[qb * 2 + 1], qpar);
         tc_fence_after();
+        bool o_waited[2] = {item_cnt == 0, item_cnt == 0};   // O_t of the previous item read by its epilogue?
         const uint32_t vbase = vcnt_wait;   // V tile j of this item has ring counter vbase + j
         for (int j = 0; j <= nmax; ++j) {
           int kst = 0;
@@ -609,6 +631,10 @@ __global__ void __launch_bounds__(A_THREADS, 1)
               }
               mbar_wait(&p_full[1], pcnt[1] & 1);
               ++pcnt[1];
+              if (!o_waited[1]) {
+                mbar_wait(&o_free[1], (item_cnt - 1) & 1);
+                o_waited[1] = true;
+              }
               tc_fence_after();
               issue_pv(1, vc % NS, j - 1 > 0);
               if (j - 1 == n1 - 1) commit(&o_full[1]);
@@ -633,11 +659,18 @@ __global__ void __launch_bounds__(A_THREADS, 1)
             }
             mbar_wait(&p_full[0], pcnt[0] & 1);
             ++pcnt[0];
+            if (!o_waited[0]) {
+              mbar_wait(&o_free[0], (item_cnt - 1) & 1);
+              o_waited[0] = true;
+            }
             tc_fence_after();
             issue_pv(0, vc % NS, j > 0);
             if (j == n0 - 1) commit(&o_full[0]);
           }
         }
+        // a tile without key tiles in this item issued no P.V: consume its o_free phase all the same (one per item)
+        for (int t = 0; t < 2; ++t)
+          if (!o_waited[t]) mbar_wait(&o_free[t], (item_cnt - 1) & 1);
       }
     }
   } else if (warp >= 4) {
@@ -650,14 +683,13 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     const uint32_t lane_base = uint32_t(quad * 32) << 16;
     const uint32_t tS = tmem_base + lane_base + (t == 0 ? Cfg::TM_S0 : Cfg::TM_S1);
     const uint32_t tO = tmem_base + lane_base + (t == 0 ? Cfg::TM_O0 : Cfg::TM_O1);
-    uint8_t* stage = sQ + t * Cfg::TILE_BYTES;
     uint32_t item_cnt = 0, scnt = 0, ocnt = 0;
     // Everything the per-step loop touches is resolved ONCE here: 32-bit shared-window addresses of its barriers
     // (a generic pointer costs an S2UR + uniform ALU chain per use), the scale, and per item the first step that
     // needs a mask.  The ncu source view of round 2 showed ~900 of the ~3800 cycles of a (2 x 128 rows) x 128 keys
     // step going to such scalar set-up on the softmax warps' critical path (profiles/README.md).
     const uint32_t a_sfull = smem_u32(&s_full[t]), a_pfull = smem_u32(&p_full[t]), a_ofull = smem_u32(&o_full[t]);
-    const uint32_t a_qfull = smem_u32(&q_full[t]);
+    const uint32_t a_ofree = smem_u32(&o_free[t]);
     // MUFU turn-taking (TURNS): the exponentials of one 128 x 128 score tile keep the MUFU unit of an SM sub-partition
     // busy for ~1050 cycles.  The two softmax warps of a sub-partition (one per query tile) take turns on it - tile
     // 0's warp runs exp(j), then tile 1's exp(j), then tile 0's exp(j+1) ... - so that the load / max / store /
@@ -674,6 +706,8 @@ __global__ void __launch_bounds__(A_THREADS, 1)
       const WorkItem w = decode_item(p, item);
       const int n = w.n[t];
       const int n_other = w.n[1 - t];
+      const int qb = (int)(item_cnt % QB);
+      uint8_t* stage = sQ + (qb * 2 + t) * Cfg::TILE_BYTES;    // this item's Q_t tile doubles as the staging tile of O_t
       const long long qpos = w.qpos[t] + row;           // global position of this thread's query row
       // first key tile (GLOBAL index) that needs a mask: the diagonal ones (kv_pos0 + 128 g + 127 > position of the
       // tile's row 0) and the ragged last one
@@ -800,7 +834,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         ++ocnt;
         tc_fence_after();
       } else {
-        mbar_wait_a(a_qfull, item_cnt & 1);   // the Q load into the staging tile must have landed
+        mbar_wait(&q_full[qb * 2 + t], (item_cnt / QB) & 1);   // the Q load into the staging tile must have landed
       }
 #pragma unroll 1
       for (int c = 0; c < D / 32; ++c) {
@@ -808,7 +842,17 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         if (n > 0) {
           tmem_ld32(tO + c * 32, o);
           tmem_wait_ld();
+          if (c == D / 32 - 1) {
+            // O_t is in registers: the next item's first P.V may overwrite the accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(a_ofree);
+          }
         } else {
+          if (c == D / 32 - 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(a_ofree);
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = 0u;
         }
@@ -837,7 +881,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           tma_store_commit();
           tma_store_wait_read0();
         }
-        mbar_arrive(&q_empty[t]);   // Q_t / staging tile may be overwritten by the next item's Q load
+        mbar_arrive(&q_empty[qb * 2 + t]);   // this Q_t / staging tile may be overwritten by a later item's Q load
       }
     }
     if (wg_tid == 0) tma_store_wait_all0();

@@ -22,12 +22,19 @@
 
 namespace lv {
 
-constexpr int G_BM = 128, G_BN = 256, G_BK = 64, G_STAGES = 4;
+constexpr int G_BM = 128, G_BK = 64, G_STAGES = 4;
 constexpr int G_A_BYTES = G_BM * G_BK * 2;          // 16 KB
-constexpr int G_B_BYTES = G_BN * G_BK * 2;          // 32 KB
 constexpr int G_C_BYTES = G_BM * 64 * 2;            // 16 KB staging per 64-column chunk
-constexpr int G_SMEM = G_STAGES * (G_A_BYTES + G_B_BYTES) + 2 * G_C_BYTES + 256 + 1024;  // + barriers + align slack
 constexpr int G_THREADS = 192;
+// The N-tile width is a template parameter: 256 (UMMA 128x256x16, the default: least shared-memory traffic per flop)
+// or 128.  With few M-blocks - a context-parallel rank holds S / cp tokens - 128 x 256 tiles can leave the last wave
+// of the persistent grid mostly empty (M = 2304, N = 5120: 360 tiles on 148 SMs = 2.43 waves); 128 x 128 tiles
+// quantise finer (720 tiles = 4.86 waves).  launch_gemm picks the width with the better wave efficiency.
+template <int BN>
+struct GemmCfg {
+  static constexpr int B_BYTES = BN * G_BK * 2;     // 32 KB / 16 KB
+  static constexpr int SMEM = G_STAGES * (G_A_BYTES + B_BYTES) + 2 * G_C_BYTES + 256 + 1024;  // + barriers + align slack
+};
 
 __device__ __forceinline__ float act_apply(float t, int act) {
   if (act == 1) return 0.5f * t * (1.f + erff(t * 0.70710678118654752440f));
@@ -48,10 +55,12 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
   nb = r / gsz;
 }
 
+template <int G_BN>
 __global__ void __launch_bounds__(G_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __nv_bfloat16* __restrict__ bias, int M, int N,
                      int K, int act, int gm) {
+  constexpr int G_B_BYTES = GemmCfg<G_BN>::B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -171,7 +180,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
         // gate_i and up_i; out[:, i] = bf16(silu(bf16 gate)) * bf16(up) - the exact rounding sequence of
         // the un-fused GEMM + lv_swiglu pair - and the stored tile is 128 columns wide.
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < G_BN / 128; ++cc) {
           uint32_t packed[32];
 #pragma unroll
           for (int hlf = 0; hlf < 2; ++hlf) {
@@ -180,7 +189,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
             tmem_ld32(taddr, r0);
             tmem_ld32(taddr + 32, r1);
             tmem_wait_ld();
-            if (cc == 1 && hlf == 1) {
+            if (cc == G_BN / 128 - 1 && hlf == 1) {
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -459,8 +468,10 @@ static int launch_gemv(const void* A, const void* W, const void* bias, void* C, 
   return LV_OK;
 }
 
-static int launch_gemm(const void* A, const void* W, const void* bias, void* C, int64_t M, int64_t N, int64_t K,
-                       int64_t lda, int64_t ldw, int64_t ldc, int act, cudaStream_t s) {
+template <int G_BN>
+static int launch_gemm_t(const void* A, const void* W, const void* bias, void* C, int64_t M, int64_t N, int64_t K,
+                         int64_t lda, int64_t ldw, int64_t ldc, int act, cudaStream_t s) {
+  constexpr int G_SMEM = GemmCfg<G_BN>::SMEM;
   CUtensorMap tmA, tmB, tmC;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -486,7 +497,7 @@ static int launch_gemm(const void* A, const void* W, const void* bias, void* C, 
   static PerDeviceOnce attr_once;
   int attr_dev;
   if (attr_once.needed(&attr_dev)) {
-    LV_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+    LV_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<G_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     attr_once.done(attr_dev);
   }
   const int64_t tiles = ((M + G_BM - 1) / G_BM) * ((N + G_BN - 1) / G_BN);
@@ -499,10 +510,35 @@ static int launch_gemm(const void* A, const void* W, const void* bias, void* C, 
     const int v = e ? atoi(e) : 16;
     return (v >= 1 && v <= 256) ? v : 16;
   }();
-  gemm_bf16_kernel<<<grid, G_THREADS, G_SMEM, s>>>(tmA, tmB, tmC, reinterpret_cast<const __nv_bfloat16*>(bias), (int)M,
-                                                   (int)N, (int)K, act, gm);
+  gemm_bf16_kernel<G_BN><<<grid, G_THREADS, G_SMEM, s>>>(tmA, tmB, tmC, reinterpret_cast<const __nv_bfloat16*>(bias), (int)M,
+                                                         (int)N, (int)K, act, gm);
   LV_CHECK_LAUNCH("gemm_bf16_kernel");
   return LV_OK;
+}
+
+// Fraction of the persistent grid's tile slots that do work: tiles / (waves * SMs).
+static double wave_efficiency(int64_t tiles, int sms) {
+  const int64_t waves = (tiles + sms - 1) / sms;
+  return (double)tiles / (double)(waves * sms);
+}
+
+static int launch_gemm(const void* A, const void* W, const void* bias, void* C, int64_t M, int64_t N, int64_t K,
+                       int64_t lda, int64_t ldw, int64_t ldc, int act, cudaStream_t s) {
+  // LV_GEMM_BN=128 / 256 forces the N-tile width (A/B runs); default: 256 unless 128 quantises >= 8 % better
+  static const int bn_env = [] {
+    const char* e = getenv("LV_GEMM_BN");
+    const int v = e ? atoi(e) : 0;
+    return (v == 128 || v == 256) ? v : 0;
+  }();
+  int bn = bn_env;
+  if (bn == 0) {
+    const int64_t mb = (M + G_BM - 1) / G_BM;
+    const double e256 = wave_efficiency(mb * ((N + 255) / 256), sm_count());
+    const double e128 = wave_efficiency(mb * ((N + 127) / 128), sm_count());
+    bn = (e128 > 1.08 * e256) ? 128 : 256;
+  }
+  if (bn == 128) return launch_gemm_t<128>(A, W, bias, C, M, N, K, lda, ldw, ldc, act, s);
+  return launch_gemm_t<256>(A, W, bias, C, M, N, K, lda, ldw, ldc, act, s);
 }
 
 }  // namespace lv

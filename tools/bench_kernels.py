@@ -96,6 +96,8 @@ def bench_gemm(results, quick):
         ("llm_down", 16384, 5120, 13824), ("vit_qkv", 65600, 3072, 1024), ("vit_proj", 65600, 1024, 1024),
         ("vit_fc1", 65600, 4096, 1024), ("vit_fc2", 65600, 1024, 4096), ("lm_head_m2", 2, 152064, 5120),
         ("square8k", 8192, 8192, 8192),
+        # one context-parallel rank of 8 on the 18K prompt (2304 tokens): few M-blocks, wave quantisation matters
+        ("cp8_qkv", 2304, 7168, 5120), ("cp8_o", 2304, 5120, 5120), ("cp8_gate_up", 2304, 27648, 5120), ("cp8_down", 2304, 5120, 13824),
     ]
     for name, M, N, K in shapes:
         x = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)

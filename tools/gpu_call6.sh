@@ -31,3 +31,25 @@ $T 400 ncu --set full --clock-control none --import-source on -k regex:attn_fwd 
 echo "== ncu attn lean exit $?"; tail -2 gpurun_out/ncu_attn_lean.log
 $T 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/c6_bench_n1.json 2> gpurun_out/c6_bench_n1.err
 echo "== bench exit $?"; tail -3 gpurun_out/c6_bench_n1.err; cut -c1-300 gpurun_out/c6_bench_n1.json
+# backward kernel: speed + one ncu capture of each pass (source view for the next optimisation step)
+$T 200 python tools/bench_bwd.py > gpurun_out/c6_bwd.log 2>&1
+echo "== bwd exit $?"; tail -n 3 gpurun_out/c6_bwd.log
+cat > /tmp/bwd16k.py <<'PY'
+import torch, sys
+sys.path.insert(0, '.')
+from long_vita_b200 import ops
+S = 16384
+q = torch.randn(1, S, 40, 128, device='cuda', dtype=torch.bfloat16)
+k = torch.randn(1, S, 8, 128, device='cuda', dtype=torch.bfloat16)
+v = torch.randn(1, S, 8, 128, device='cuda', dtype=torch.bfloat16)
+out, lse = ops.attention_fwd(q, k, v, causal=True, return_lse=True)
+do = torch.randn_like(out)
+for _ in range(2):
+    ops.attention_bwd(do, q, k, v, out, lse, causal=True)
+torch.cuda.synchronize()
+PY
+$T 500 ncu --set full --clock-control none --import-source on -k regex:attn_bwd2 -s 2 -c 2 -f -o gpurun_out/r2_bwd16k python /tmp/bwd16k.py > gpurun_out/ncu_bwd.log 2>&1
+echo "== ncu bwd exit $?"; tail -2 gpurun_out/ncu_bwd.log
+# DRAM traffic of the dominant kernel inside the bench step (roofline.traffic): the QKV / O / gate|up / down GEMMs of one decoder layer
+$T 600 ncu --set full --clock-control none -k regex:gemm_bf16 -s 103 -c 8 -f -o gpurun_out/r2_bench_gemm python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-attn-probe > gpurun_out/ncu_bench_gemm.log 2>&1
+echo "== ncu bench gemm exit $?"; tail -2 gpurun_out/ncu_bench_gemm.log
