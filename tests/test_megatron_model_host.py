@@ -240,6 +240,9 @@ class _GlooCPContext:
     def qkv_buffer(self):
         return self.buf
 
+    def check(self):
+        """cp.CPContext.check reads the exchange's fault word; a gloo all-gather cannot time out silently."""
+
     def attention(self, out=None, scale=None):
         from oracle import ops as O
 
