@@ -187,17 +187,20 @@ __device__ __forceinline__ float ex2_poly(float x) {
 template <bool POLY>
 __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&sc)[32], float scale_log2, float neg_m, float& l0,
                                                   float& l1, float& l2, float& l3, uint32_t (&pk)[16]) {
+  // per 4 scores: 2 FFMA2 (x = s * scale - m), 4 MUFU.EX2, 2 FADD2 (four partial row sums), 2 packs - 2.5 instructions
+  // per element around the 8-cycle MUFU slot instead of 3.5 with scalar FFMA / FADD (same roundings: the packed forms
+  // are two independent IEEE operations)
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
-    const float p0 = ex2(fmaf(__uint_as_float(sc[i + 0]), scale_log2, neg_m));
-    const float p1 = ex2(fmaf(__uint_as_float(sc[i + 1]), scale_log2, neg_m));
-    const float p2 = ex2(fmaf(__uint_as_float(sc[i + 2]), scale_log2, neg_m));
-    const float x3 = fmaf(__uint_as_float(sc[i + 3]), scale_log2, neg_m);
+    float x0, x1, x2, x3;
+    ffma2(x0, x1, __uint_as_float(sc[i + 0]), __uint_as_float(sc[i + 1]), scale_log2, neg_m);
+    ffma2(x2, x3, __uint_as_float(sc[i + 2]), __uint_as_float(sc[i + 3]), scale_log2, neg_m);
+    const float p0 = ex2(x0);
+    const float p1 = ex2(x1);
+    const float p2 = ex2(x2);
     const float p3 = POLY ? ex2_poly(x3) : ex2(x3);
-    l0 += p0;
-    l1 += p1;
-    l2 += p2;
-    l3 += p3;
+    fadd2(l0, l1, l0, l1, p0, p1);
+    fadd2(l2, l3, l2, l3, p2, p3);
     pk[i / 2] = pack_bf16(p0, p1);
     pk[i / 2 + 1] = pack_bf16(p2, p3);
   }
@@ -681,22 +684,22 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     const int row = quad * 32 + lane;             // row inside the 128-row tile
     const int wg_tid = (warp - 4 - 4 * t) * 32 + lane;
     const uint32_t lane_base = uint32_t(quad * 32) << 16;
-    const uint32_t tS = tmem_base + lane_base + (t == 0 ? Cfg::TM_S0 : Cfg::TM_S1);
-    const uint32_t tO = tmem_base + lane_base + (t == 0 ? Cfg::TM_O0 : Cfg::TM_O1);
+    const uint32_t tS = keep_u32(tmem_base + lane_base + (t == 0 ? Cfg::TM_S0 : Cfg::TM_S1));
+    const uint32_t tO = keep_u32(tmem_base + lane_base + (t == 0 ? Cfg::TM_O0 : Cfg::TM_O1));
     uint32_t item_cnt = 0, scnt = 0, ocnt = 0;
     // Everything the per-step loop touches is resolved ONCE here: 32-bit shared-window addresses of its barriers
     // (a generic pointer costs an S2UR + uniform ALU chain per use), the scale, and per item the first step that
     // needs a mask.  The ncu source view of round 2 showed ~900 of the ~3800 cycles of a (2 x 128 rows) x 128 keys
     // step going to such scalar set-up on the softmax warps' critical path (profiles/README.md).
-    const uint32_t a_sfull = smem_u32(&s_full[t]), a_pfull = smem_u32(&p_full[t]), a_ofull = smem_u32(&o_full[t]);
-    const uint32_t a_ofree = smem_u32(&o_free[t]);
+    const uint32_t a_sfull = keep_u32(smem_u32(&s_full[t])), a_pfull = keep_u32(smem_u32(&p_full[t]));
+    const uint32_t a_ofull = keep_u32(smem_u32(&o_full[t])), a_ofree = keep_u32(smem_u32(&o_free[t]));
     // MUFU turn-taking (TURNS): the exponentials of one 128 x 128 score tile keep the MUFU unit of an SM sub-partition
     // busy for ~1050 cycles.  The two softmax warps of a sub-partition (one per query tile) take turns on it - tile
     // 0's warp runs exp(j), then tile 1's exp(j), then tile 0's exp(j+1) ... - so that the load / max / store /
     // hand-off parts of one warp overlap the exp phase of the other instead of both exp phases colliding.
     // tok[t][quad] is arrived by the OTHER tile's warp when its exp phase ends; waits and arrivals are paired exactly
     // (both sides know n[0], n[1] of the item).
-    const uint32_t a_tok_mine = smem_u32(&tok[t * 4 + quad]), a_tok_other = smem_u32(&tok[(1 - t) * 4 + quad]);
+    const uint32_t a_tok_mine = keep_u32(smem_u32(&tok[t * 4 + quad])), a_tok_other = keep_u32(smem_u32(&tok[(1 - t) * 4 + quad]));
     uint32_t tok_cnt = 0;
     const float scale_log2 = p.scale_log2;
     const int n_kv_tiles = (p.sk + A_BN - 1) / A_BN;
@@ -731,7 +734,11 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         tmem_wait_ld();
 
         // ---- mask (only diagonal tiles and the ragged last key tile) ----
-        int live = 4;      // 32-column chunks with at least one visible key for some row of this warp (warp-uniform)
+        // 32-column chunks with at least one visible key for some row of this warp (warp-uniform).  Only tracked at
+        // head_dim 64 (the ViT's ragged 1025-key rows: 1 live chunk of 4 in every 9th tile); at head_dim 128 the test
+        // per chunk costs more on every step than the skipped exponentials save on the rare diagonal tile.
+        constexpr bool SKIP_DEAD = (D == 64);
+        int live = 4;
         if (g >= j_mask) {
           const long long kidx0 = (long long)g * A_BN;
           long long lim = p.sk - kidx0;                               // first invalid column (ragged)
@@ -748,8 +755,10 @@ __global__ void __launch_bounds__(A_THREADS, 1)
             if (i >= ilim) s[i] = 0xff800000u;  // -inf
           // chunks beyond the warp's last visible column hold only masked scores: their exponentials are skipped
           // (P = 0).  The ragged last key tile of the ViT (1025 = 8 x 128 + 1 keys) costs 1 chunk instead of 4.
-          const int lw = __shfl_sync(0xffffffffu, lim_warp < 0 ? 0 : (lim_warp > A_BN ? A_BN : (int)lim_warp), 0);
-          live = (lw + 31) >> 5;
+          if (SKIP_DEAD) {
+            const int lw = __shfl_sync(0xffffffffu, lim_warp < 0 ? 0 : (lim_warp > A_BN ? A_BN : (int)lim_warp), 0);
+            live = (lw + 31) >> 5;
+          }
         }
 
         // ---- row max: 8 independent chains ----
@@ -803,7 +812,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
           uint32_t pk[32];
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            if (2 * h + c < live) {
+            if (!SKIP_DEAD || 2 * h + c < live) {
               softmax_exp_chunk<POLY>(reinterpret_cast<const uint32_t(&)[32]>(s[(2 * h + c) * 32]), scale_log2, neg_m, l0, l1, l2, l3,
                                       reinterpret_cast<uint32_t(&)[16]>(pk[c * 16]));
             } else {
@@ -1381,9 +1390,9 @@ static int launch_attn_t(const lv_attn_params* a, const CpKParams* cp, cudaStrea
   return LV_OK;
 }
 
-// LV_ATTN_TURNS=0 / 1 forces the MUFU turn-taking of the softmax warps off / on (default: on at head_dim 128, where
-// the step is latency-bound; off at head_dim 64, where the MUFU is the bottleneck outright and two warps per
-// sub-partition use it better than one).  LV_ATTN_POLY=1: every 4th exponential on the FMA pipe.
+// LV_ATTN_TURNS=1 switches the MUFU turn-taking of the softmax warps on (default off: with two warps per sub-partition
+// interleaving on the MUFU, 128K causal measured 1137 TFLOP/s without turns and 1076 with).  LV_ATTN_POLY=1: every
+// 4th exponential on the FMA pipe.
 static int attn_turns_env() {
   static const int v = [] {
     const char* e = getenv("LV_ATTN_TURNS");
@@ -1397,7 +1406,7 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
   if constexpr (VER == 2) {
     return launch_attn_t<D, CP, 2>(a, cp, s);
   } else {
-    const bool turns = attn_turns_env() >= 0 ? attn_turns_env() == 1 : (D == 128);
+    const bool turns = attn_turns_env() == 1;      // measured round 2: off is faster at both head dims (profiles/README.md)
     if constexpr (CP) {     // context-parallel launches: the default pair only (fewer instantiations of the big kernel)
       return turns ? launch_attn_t<D, CP, 1, false, true>(a, cp, s) : launch_attn_t<D, CP, 1, false, false>(a, cp, s);
     } else {

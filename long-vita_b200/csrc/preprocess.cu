@@ -107,10 +107,10 @@ extern "C" int64_t lv_frame_preprocess_ws_bytes(int64_t n_frames, int64_t H, int
 extern "C" int lv_frame_preprocess(const void* frames, void* out, void* ws, const int32_t* win_min, const int32_t* win_cnt,
                                    const int32_t* coeff, int64_t ksize, int64_t n_frames, int64_t H, int64_t W, int64_t S,
                                    const int32_t* background, const float* mean, const float* std, lv_stream_t stream) {
-  LV_CHECK_ARG(frames && out && ws && win_min && win_cnt && coeff && background && mean && std, "lv_frame_preprocess: null pointer");
   LV_CHECK_ARG(n_frames >= 0 && H > 0 && W > 0 && S > 0 && ksize > 0, "lv_frame_preprocess: empty shape");
   LV_CHECK_ARG(H < (1 << 15) && W < (1 << 15) && S < (1 << 15), "lv_frame_preprocess: image side too large");
-  if (n_frames == 0) return LV_OK;
+  if (n_frames == 0) return LV_OK;      // an empty batch has no buffers to check
+  LV_CHECK_ARG(frames && out && ws && win_min && win_cnt && coeff && background && mean && std, "lv_frame_preprocess: null pointer");
   LV_BIND_DEVICE(frames);
   const int n = (int)(H > W ? H : W);
   const int top = W > H ? (int)((W - H) / 2) : 0;       // expand2square: result.paste(img, (0, (width - height) // 2))
