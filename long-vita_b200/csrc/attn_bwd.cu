@@ -675,6 +675,21 @@ __global__ void __launch_bounds__(B2_THREADS, 1)
         }
         const long long row0_pos = row_pos - row;
         const bool need_mask = p.causal && (MODE == 0 ? (row0_pos + 127 > col_pos0) : (col_pos0 + 63 > row0_pos));
+        // Columns this thread keeps: [c_lo, c_hi) of the 64 of this half.  Interior tiles (no causal boundary, no
+        // ragged edge) keep everything and take the branch-free path below - the round-2 ncu source view showed a
+        // third of the element-wise samples on per-element 64-bit compares and selects that only diagonal tiles need.
+        int c_lo = 0, c_hi = col_valid < 64 ? (col_valid < 0 ? 0 : col_valid) : 64;
+        if (need_mask) {
+          const long long dlt = row_pos - col_pos0;                      // MODE 0: keep c >= dlt; MODE 1: keep c <= dlt
+          if (MODE == 0) {
+            c_lo = dlt <= 0 ? 0 : (dlt > 64 ? 64 : (int)dlt);
+          } else {
+            const int hi = dlt < 0 ? 0 : (dlt >= 64 ? 64 : (int)dlt + 1);
+            c_hi = hi < c_hi ? hi : c_hi;
+          }
+        }
+        const bool masked_tile = need_mask || col_valid < 64;           // warp-uniform (tile-level quantities)
+        const float sc_log2 = p.scale_log2, sc = p.scale;
 #pragma unroll 1
         for (int c2 = 0; c2 < 2; ++c2) {
           uint32_t sv[32], dv[32];
@@ -682,23 +697,44 @@ __global__ void __launch_bounds__(B2_THREADS, 1)
           tmem_ld32(tB + c2 * 32, dv);
           tmem_wait_ld();
           uint32_t pp[16], ds[16];
+          if (!masked_tile) {
 #pragma unroll
-          for (int k = 0; k < 32; k += 2) {
-            float pv[2], dsv[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int c = c2 * 32 + k + e;
-              const float l2 = (MODE == 0) ? s_lse[st * 128 + b * 64 + c] : row_lse2;
-              const float dl = (MODE == 0) ? s_dlt[st * 128 + b * 64 + c] : row_delta;
-              float pe = ex2(fmaf(__uint_as_float(sv[k + e]), p.scale_log2, -l2));
-              bool keep = c < col_valid;
-              if (need_mask) keep = keep && (MODE == 0 ? (row_pos <= col_pos0 + c) : (col_pos0 + c <= row_pos));
-              pe = keep ? pe : 0.f;
-              pv[e] = pe;
-              dsv[e] = pe * (__uint_as_float(dv[k + e]) - dl) * p.scale;
+            for (int k = 0; k < 32; k += 2) {
+              const int c = c2 * 32 + k;
+              float l2a, l2b, dla, dlb;
+              if (MODE == 0) {
+                l2a = s_lse[st * 128 + b * 64 + c];
+                l2b = s_lse[st * 128 + b * 64 + c + 1];
+                dla = s_dlt[st * 128 + b * 64 + c];
+                dlb = s_dlt[st * 128 + b * 64 + c + 1];
+              } else {
+                l2a = l2b = row_lse2;
+                dla = dlb = row_delta;
+              }
+              const float p0 = ex2(fmaf(__uint_as_float(sv[k]), sc_log2, -l2a));
+              const float p1 = ex2(fmaf(__uint_as_float(sv[k + 1]), sc_log2, -l2b));
+              float d0, d1;
+              fadd2(d0, d1, __uint_as_float(dv[k]), __uint_as_float(dv[k + 1]), -dla, -dlb);
+              pp[k / 2] = pack_bf16(p0, p1);
+              ds[k / 2] = pack_bf16(p0 * d0 * sc, p1 * d1 * sc);
             }
-            pp[k / 2] = pack_bf16(pv[0], pv[1]);
-            ds[k / 2] = pack_bf16(dsv[0], dsv[1]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) {
+              float pv[2], dsv[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int c = c2 * 32 + k + e;
+                const float l2 = (MODE == 0) ? s_lse[st * 128 + b * 64 + c] : row_lse2;
+                const float dl = (MODE == 0) ? s_dlt[st * 128 + b * 64 + c] : row_delta;
+                float pe = ex2(fmaf(__uint_as_float(sv[k + e]), sc_log2, -l2));
+                pe = (c >= c_lo && c < c_hi) ? pe : 0.f;
+                pv[e] = pe;
+                dsv[e] = pe * (__uint_as_float(dv[k + e]) - dl) * sc;
+              }
+              pp[k / 2] = pack_bf16(pv[0], pv[1]);
+              ds[k / 2] = pack_bf16(dsv[0], dsv[1]);
+            }
           }
           if (MODE == 0) tmem_st16(tA + c2 * 16, pp);
           tmem_st16(tB + c2 * 16, ds);

@@ -503,13 +503,20 @@ static int launch_gemm_t(const void* A, const void* W, const void* bias, void* C
   const int64_t tiles = ((M + G_BM - 1) / G_BM) * ((N + G_BN - 1) / G_BN);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   // M-blocks per rasterisation group: the A panel of a group (gm x 128 rows x K) stays in L2 while its tiles sweep
-  // the N-blocks, and W is re-read from HBM once per group.  16 measured 969 MB of DRAM traffic on the QKV GEMM
-  // (476 MB algorithmic); LV_GEMM_GM=32 halves the W re-reads (A panel 42 MB at K = 5120, still L2-resident).
-  static const int gm = [] {
+  // the N-blocks, and W is re-read from HBM once per group, so DRAM traffic ~ A + C + (num_m / gm) * W.  Round 2 ncu
+  // inside the bench step, gm = 16: QKV 1107 MB vs 526 MB algorithmic, gate|up 3248 vs 982, down (K = 13824: a 57 MB
+  // panel, A is re-read too) 3096 vs 840.  The group is sized so that the A panel takes ~40 MB of the 126 MB L2
+  // whatever K is (K = 5120 -> 30 M-blocks, K = 13824 -> 11); LV_GEMM_GM forces a value for A/B runs.
+  static const int gm_env = [] {
     const char* e = getenv("LV_GEMM_GM");
-    const int v = e ? atoi(e) : 16;
-    return (v >= 1 && v <= 256) ? v : 16;
+    const int v = e ? atoi(e) : 0;
+    return (v >= 1 && v <= 256) ? v : 0;
   }();
+  int gm = gm_env;
+  if (gm == 0) {
+    gm = (int)((40ll << 20) / (256 * K));
+    gm = gm < 8 ? 8 : (gm > 64 ? 64 : gm);
+  }
   gemm_bf16_kernel<G_BN><<<grid, G_THREADS, G_SMEM, s>>>(tmA, tmB, tmC, reinterpret_cast<const __nv_bfloat16*>(bias), (int)M,
                                                          (int)N, (int)K, act, gm);
   LV_CHECK_LAUNCH("gemm_bf16_kernel");
