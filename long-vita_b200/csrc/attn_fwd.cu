@@ -184,21 +184,53 @@ __device__ __forceinline__ float ex2_poly(float x) {
 // One 32-column chunk of a score row: P = 2^(S * scale_log2 - m), four partial row sums, bf16 pack.
 // POLY: every 4th exponential is evaluated on the FMA pipe (ex2_poly), relieving the MUFU pipe that both
 // softmax warpgroups share (16 ex2 / clk / SM = as many cycles as the two MMAs of a step at d = 128).
-template <bool POLY>
+// Two exponentials at once on the FMA / ALU pipes with packed fp32 arithmetic (ex2_poly for a pair): 2 FMNMX (clamp),
+// 3 FADD2 (magic-number split x = n + f), 3 FFMA2 (cubic), 2 LEA (exponent insert) = 5 issue slots per element and no
+// MUFU slot, against 8 MUFU cycles per element otherwise.
+__device__ __forceinline__ void ex2_poly_pair(float x0, float x1, float& p0, float& p1) {
+  x0 = fmaxf(x0, -125.f);
+  x1 = fmaxf(x1, -125.f);
+  float t0, t1, n0, n1, f0, f1;
+  fadd2(t0, t1, x0, x1, 12582912.f, 12582912.f);
+  fadd2(n0, n1, t0, t1, -12582912.f, -12582912.f);
+  fadd2(f0, f1, x0, x1, -n0, -n1);
+  float q0, q1;
+  ffma2v(q0, q1, f0, f1, 0.055171321f, 0.055171321f, 0.24261054f, 0.24261054f);
+  ffma2v(q0, q1, q0, q1, f0, f1, 0.69326099f, 0.69326099f);
+  ffma2v(q0, q1, q0, q1, f0, f1, 0.99992811f, 0.99992811f);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
+// One 32-column chunk of a score row: P = 2^(S * scale_log2 - m), four partial row sums, bf16 pack.
+// POLY = number of element PAIRS per 8 (16 elements) whose exponentials run on the FMA pipe instead of the MUFU:
+// 0 (none), 2 (25 %), 3 (37.5 %), 4 (50 %).  The MUFU unit delivers 4 results per cycle per SM sub-partition - a 128 x
+// 128 tile keeps it busy 1024 cycles, as long as the tile's two MMAs - and is the softmax's bottleneck; the packed
+// fp32 forms (2.5 issue slots per MUFU element, 6.5 per polynomial one) leave room to move part of the work over.
+template <int POLY>
 __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&sc)[32], float scale_log2, float neg_m, float& l0,
                                                   float& l1, float& l2, float& l3, uint32_t (&pk)[16]) {
-  // per 4 scores: 2 FFMA2 (x = s * scale - m), 4 MUFU.EX2, 2 FADD2 (four partial row sums), 2 packs - 2.5 instructions
-  // per element around the 8-cycle MUFU slot instead of 3.5 with scalar FFMA / FADD (same roundings: the packed forms
-  // are two independent IEEE operations)
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     float x0, x1, x2, x3;
     ffma2(x0, x1, __uint_as_float(sc[i + 0]), __uint_as_float(sc[i + 1]), scale_log2, neg_m);
     ffma2(x2, x3, __uint_as_float(sc[i + 2]), __uint_as_float(sc[i + 3]), scale_log2, neg_m);
-    const float p0 = ex2(x0);
-    const float p1 = ex2(x1);
-    const float p2 = ex2(x2);
-    const float p3 = POLY ? ex2_poly(x3) : ex2(x3);
+    // pairs are numbered 0..7 inside a 16-element window; which of them take the polynomial is a compile-time pattern
+    const int pair_a = (i / 2) & 7, pair_b = (i / 2 + 1) & 7;
+    constexpr unsigned pattern = POLY == 2 ? 0x44u : (POLY == 3 ? 0x54u : (POLY == 4 ? 0xAAu : 0u));
+    float p0, p1, p2, p3;
+    if ((pattern >> pair_a) & 1u) {
+      ex2_poly_pair(x0, x1, p0, p1);
+    } else {
+      p0 = ex2(x0);
+      p1 = ex2(x1);
+    }
+    if ((pattern >> pair_b) & 1u) {
+      ex2_poly_pair(x2, x3, p2, p3);
+    } else {
+      p2 = ex2(x2);
+      p3 = ex2(x3);
+    }
     fadd2(l0, l1, l0, l1, p0, p1);
     fadd2(l2, l3, l2, l3, p2, p3);
     pk[i / 2] = pack_bf16(p0, p1);
@@ -206,11 +238,14 @@ __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&sc)[32], floa
   }
 }
 
-// LV_ATTN_POLY=1: softmax exponentials split 3:1 between MUFU (ex2.approx) and the FMA pipe.
+// Exponentials on the FMA pipe, in element pairs per 8 pairs: LV_ATTN_POLY = 0 | 2 | 3 | 4 (default ATTN_POLY_DEFAULT).
+constexpr int ATTN_POLY_DEFAULT = 0;
 static int attn_poly_exp() {
   static const int v = [] {
     const char* e = getenv("LV_ATTN_POLY");
-    return (e != nullptr && e[0] == '1') ? 1 : 0;
+    if (e == nullptr) return ATTN_POLY_DEFAULT;
+    const int x = atoi(e);
+    return (x == 0 || x == 2 || x == 3 || x == 4) ? x : (x == 1 ? 2 : ATTN_POLY_DEFAULT);
   }();
   return v;
 }
@@ -428,7 +463,7 @@ __device__ __forceinline__ WorkItem decode_item(const AttnKParams& p, int item) 
 
 // POLY: every 4th exponential on the FMA pipe (ex2_poly).  TURNS: MUFU turn-taking of the two softmax warps of an
 // SM sub-partition (see the softmax section).  Both are compile-time so the per-step loop carries no flag tests.
-template <int D, bool CP, bool POLY, bool TURNS>
+template <int D, bool CP, int POLY, bool TURNS>
 __global__ void __launch_bounds__(A_THREADS, 1)
     attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -1226,9 +1261,9 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         for (int c = 0; c < 2; ++c) {
           uint32_t pk[16];
           if (p.poly_exp)
-            softmax_exp_chunk<true>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
+            softmax_exp_chunk<2>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
           else
-            softmax_exp_chunk<false>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
+            softmax_exp_chunk<0>(s[c], p.scale_log2, neg_m, l0, l1, l2, l3, pk);
           tmem_st16(tS + b * 64 + c * 16, pk);
         }
         l += (l0 + l1) + (l2 + l3);
@@ -1313,7 +1348,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int D, bool CP, int VER, bool POLY = false, bool TURNS = true>
+template <int D, bool CP, int VER, int POLY = 0, bool TURNS = false>
 static int launch_attn_t(const lv_attn_params* a, const CpKParams* cp, cudaStream_t s) {
   using Cfg = AttnCfg<D>;
   CUtensorMap tmQ, tmK, tmV, tmO;
@@ -1407,12 +1442,15 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
     return launch_attn_t<D, CP, 2>(a, cp, s);
   } else {
     const bool turns = attn_turns_env() == 1;      // measured round 2: off is faster at both head dims (profiles/README.md)
-    if constexpr (CP) {     // context-parallel launches: the default pair only (fewer instantiations of the big kernel)
-      return turns ? launch_attn_t<D, CP, 1, false, true>(a, cp, s) : launch_attn_t<D, CP, 1, false, false>(a, cp, s);
+    const int poly = attn_poly_exp();              // pairs per 8 on the FMA pipe: LV_ATTN_POLY = 0 | 2 | 3 | 4
+    if constexpr (CP) {     // context-parallel launches: the default only (fewer instantiations of the big kernel)
+      return launch_attn_t<D, CP, 1, ATTN_POLY_DEFAULT, false>(a, cp, s);
     } else {
-      const bool poly = attn_poly_exp() != 0;
-      if (poly) return turns ? launch_attn_t<D, CP, 1, true, true>(a, cp, s) : launch_attn_t<D, CP, 1, true, false>(a, cp, s);
-      return turns ? launch_attn_t<D, CP, 1, false, true>(a, cp, s) : launch_attn_t<D, CP, 1, false, false>(a, cp, s);
+      if (turns) return launch_attn_t<D, CP, 1, ATTN_POLY_DEFAULT, true>(a, cp, s);
+      if (poly == 0) return launch_attn_t<D, CP, 1, 0, false>(a, cp, s);
+      if (poly == 2) return launch_attn_t<D, CP, 1, 2, false>(a, cp, s);
+      if (poly == 3) return launch_attn_t<D, CP, 1, 3, false>(a, cp, s);
+      return launch_attn_t<D, CP, 1, 4, false>(a, cp, s);
     }
   }
 }

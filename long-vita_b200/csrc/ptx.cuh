@@ -308,6 +308,15 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
       : "=f"(d0), "=f"(d1)
       : "f"(a0), "f"(a1), "f"(b), "f"(c));
 }
+// general packed fused multiply-add: (d0, d1) = (a0, a1) * (b0, b1) + (c0, c1)
+__device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
 __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
   asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
       "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
