@@ -30,6 +30,8 @@ NVCC_FLAGS = [
 
 if os.environ.get("LV_WATCHDOG") == "1":      # debug build: stuck waits report themselves and trap (csrc/ptx.cuh)
     NVCC_FLAGS.append("-DLV_WATCHDOG")
+if os.environ.get("LV_EXTRA_DEFINES"):         # experiment builds, e.g. LV_EXTRA_DEFINES="-DLV_ATTN_QBUF64=2"
+    NVCC_FLAGS.extend(os.environ["LV_EXTRA_DEFINES"].split())
 
 
 def _nvcc() -> str:
@@ -67,7 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         have = open(stamp).read().split("\n")
         # same sources; and the same flags unless the caller did not ask for a particular variant
         # (LV_WATCHDOG unset: keep whichever variant was shipped, e.g. a watchdog build made before gpurun)
-        if have[0] == digest and ("LV_WATCHDOG" not in os.environ or have[1:2] == [flags]):
+        variant_asked = "LV_WATCHDOG" in os.environ or "LV_EXTRA_DEFINES" in os.environ
+        if have[0] == digest and (not variant_asked or have[1:2] == [flags]):
             return LIB
     nvcc = _nvcc()
 

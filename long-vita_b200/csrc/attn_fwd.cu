@@ -384,7 +384,11 @@ struct AttnCfg {
   // Q tiles of two work items in flight when they fit (head_dim 64: 4 x 16 KB): the next item's Q lands while this
   // one computes, and its first Q.K^T does not wait for this item's epilogue.  Short items - the ViT's 9 key tiles per
   // (frame, head, 256 rows) - otherwise pay an exposed TMA round trip (~1.5 us) per item.
-  static constexpr int QBUF = (D == 64) ? 2 : 1;
+  // (compile-time switch while the two-item path is being validated: -DLV_ATTN_QBUF64=2)
+#ifndef LV_ATTN_QBUF64
+#define LV_ATTN_QBUF64 1
+#endif
+  static constexpr int QBUF = (D == 64) ? LV_ATTN_QBUF64 : 1;
   static constexpr int SMEM_Q = QBUF * 2 * TILE_BYTES;
   static constexpr int SMEM_K = KV_STAGES * TILE_BYTES;
   static constexpr int SMEM_V = KV_STAGES * TILE_BYTES;

@@ -531,11 +531,15 @@ static double wave_efficiency(int64_t tiles, int sms) {
 
 static int launch_gemm(const void* A, const void* W, const void* bias, void* C, int64_t M, int64_t N, int64_t K,
                        int64_t lda, int64_t ldw, int64_t ldc, int act, cudaStream_t s) {
-  // LV_GEMM_BN=128 / 256 forces the N-tile width (A/B runs); default: 256 unless 128 quantises >= 8 % better
+  // LV_GEMM_BN=128 / 256 forces the N-tile width (A/B runs).  Measured round 2 (tools/bench_kernels.py, M = 2304):
+  // 128-wide tiles run at ~0.75x the per-tile rate of 256-wide ones (UMMA 128x128x16 reads 8 KB of shared memory per
+  // 64 cycles - the full 128 B/clk - while TMA refills the ring), which costs more than the fuller last wave gains
+  // (O-proj 825 vs 1102 TFLOP/s), so 256 stays the default everywhere; LV_GEMM_BN=auto applies the wave heuristic.
   static const int bn_env = [] {
     const char* e = getenv("LV_GEMM_BN");
-    const int v = e ? atoi(e) : 0;
-    return (v == 128 || v == 256) ? v : 0;
+    if (e != nullptr && e[0] == 'a') return 0;
+    const int v = e ? atoi(e) : 256;
+    return (v == 128 || v == 256) ? v : 256;
   }();
   int bn = bn_env;
   if (bn == 0) {

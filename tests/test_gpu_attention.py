@@ -74,6 +74,12 @@ def test_attention_forward(L, sq, hq, hkv, d, causal):
     check(L, 1, sq, sq, hq, hkv, d, causal, seed=sq + d)
 
 
+def test_attention_many_items_per_cta_head_dim_64(L):
+    """ViT shape with more work items than SMs (12 frames x 16 heads x 5 query blocks = 960 on 148 CTAs): every CTA
+    walks several items, with the ragged last one (1 valid row, second tile empty) somewhere in its list."""
+    check(L, 12, 1025, 1025, 16, 16, 64, False, seed=77)
+
+
 def test_attention_batch_and_layouts(L):
     check(L, 3, 300, 300, 4, 2, 128, True, seed=1, layout="bshd")
     check(L, 2, 640, 640, 4, 4, 64, False, seed=2, layout="sbhd")
