@@ -606,6 +606,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
       const uint32_t tO[2] = {tmem_base + Cfg::TM_O0, tmem_base + Cfg::TM_O1};
       uint32_t item_cnt = 0, kcnt = 0, vcnt_wait = 0, vcnt_rel = 0;
       uint32_t pcnt[2] = {0, 0};
+      uint32_t of_cnt[2] = {0, 0};     // items so far in which tile t had key tiles (= completed o_free[t] phases)
 
       // tiles are 1024-byte aligned, so stepping a descriptor is a plain add on its 14-bit address field
       const uint64_t qdesc0 = make_smem_desc(smem_u32(sQ), 16, 1024);
@@ -651,7 +652,11 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         mbar_wait(&q_full[qb * 2 + 0], qpar);
         mbar_wait(&q_full[qb * 2 + 1], qpar);
         tc_fence_after();
-        bool o_waited[2] = {item_cnt == 0, item_cnt == 0};   // O_t of the previous item read by its epilogue?
+        // O_t of the previous item with key tiles read out by its epilogue?  o_free[t] completes one phase per item in
+        // which tile t HAS key tiles (n[t] > 0) - both sides count those items the same way.  (Counting every item
+        // let the epilogue warps of a tile without key tiles - the empty second tile of the ViT's last query block -
+        // arrive for two consecutive items before the issuer looked: a parity wait cannot tell two phases from none.)
+        bool o_waited[2] = {false, false};
         const uint32_t vbase = vcnt_wait;   // V tile j of this item has ring counter vbase + j
         for (int j = 0; j <= nmax; ++j) {
           int kst = 0;
@@ -674,7 +679,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
               mbar_wait(&p_full[1], pcnt[1] & 1);
               ++pcnt[1];
               if (!o_waited[1]) {
-                mbar_wait(&o_free[1], (item_cnt - 1) & 1);
+                if (of_cnt[1] > 0) mbar_wait(&o_free[1], (of_cnt[1] - 1) & 1);
                 o_waited[1] = true;
               }
               tc_fence_after();
@@ -702,7 +707,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
             mbar_wait(&p_full[0], pcnt[0] & 1);
             ++pcnt[0];
             if (!o_waited[0]) {
-              mbar_wait(&o_free[0], (item_cnt - 1) & 1);
+              if (of_cnt[0] > 0) mbar_wait(&o_free[0], (of_cnt[0] - 1) & 1);
               o_waited[0] = true;
             }
             tc_fence_after();
@@ -710,9 +715,8 @@ __global__ void __launch_bounds__(A_THREADS, 1)
             if (j == n0 - 1) commit(&o_full[0]);
           }
         }
-        // a tile without key tiles in this item issued no P.V: consume its o_free phase all the same (one per item)
-        for (int t = 0; t < 2; ++t)
-          if (!o_waited[t]) mbar_wait(&o_free[t], (item_cnt - 1) & 1);
+        if (n0 > 0) ++of_cnt[0];
+        if (n1 > 0) ++of_cnt[1];
       }
     }
   } else if (warp >= 4) {
@@ -897,10 +901,6 @@ __global__ void __launch_bounds__(A_THREADS, 1)
             if (lane == 0) mbar_arrive_a(a_ofree);
           }
         } else {
-          if (c == D / 32 - 1) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive_a(a_ofree);
-          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = 0u;
         }

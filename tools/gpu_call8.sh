@@ -6,6 +6,9 @@ T="timeout -k 5"
 LV_WATCHDOG=1 LV_EXTRA_DEFINES="-DLV_ATTN_QBUF64=2" $T 300 python long-vita_b200/build.py > gpurun_out/build_qbuf2.log 2>&1 || { tail -5 gpurun_out/build_qbuf2.log; exit 1; }
 $T 90 python -m pytest tests/test_gpu_attention.py -m gpu -q -x -k "many_items" --timeout 60 --timeout-method=thread > gpurun_out/c8_qbuf2.log 2>&1
 echo "== two-Q-buffer variant, many items (watchdog) exit $?"; grep -h "lv watchdog" gpurun_out/c8_qbuf2.log | sort | uniq -c | head -12; tail -n 3 gpurun_out/c8_qbuf2.log
+LV_WATCHDOG=1 LV_EXTRA_DEFINES="" $T 300 python long-vita_b200/build.py > gpurun_out/build_wd.log 2>&1 || { tail -5 gpurun_out/build_wd.log; exit 1; }
+$T 90 python -m pytest tests/test_gpu_attention.py -m gpu -q -x -k "many_items or 1025" --timeout 60 --timeout-method=thread > gpurun_out/c8_qbuf1.log 2>&1
+echo "== one-Q-buffer (default) variant, many items (watchdog) exit $?"; grep -h "lv watchdog" gpurun_out/c8_qbuf1.log | sort | uniq -c | head -12; tail -n 3 gpurun_out/c8_qbuf1.log
 LV_WATCHDOG=0 LV_EXTRA_DEFINES="" $T 300 python long-vita_b200/build.py > gpurun_out/build_release.log 2>&1 || { tail -5 gpurun_out/build_release.log; exit 1; }
 $T 240 python -m pytest tests/test_gpu_attention.py tests/test_gpu_attention_bwd.py tests/test_gpu_gemm.py tests/test_gpu_surfaces.py -m gpu -q -x --timeout 60 --timeout-method=thread > gpurun_out/c8_test_a.log 2>&1
 RC=$?; echo "== parity (default build) exit $RC"; tail -n 4 gpurun_out/c8_test_a.log
