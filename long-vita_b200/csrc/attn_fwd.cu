@@ -239,7 +239,7 @@ __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&sc)[32], floa
 }
 
 // Exponentials on the FMA pipe, in element pairs per 8 pairs: LV_ATTN_POLY = 0 | 2 | 3 | 4 (default ATTN_POLY_DEFAULT).
-constexpr int ATTN_POLY_DEFAULT = 0;
+constexpr int ATTN_POLY_DEFAULT = 2;   // measured round 2: 25 % is the best share at both head dims (profiles/README.md)
 static int attn_poly_exp() {
   static const int v = [] {
     const char* e = getenv("LV_ATTN_POLY");
