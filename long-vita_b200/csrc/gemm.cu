@@ -570,7 +570,10 @@ int lv_gemm_bias_act(const void* A, const void* W, const void* bias, void* C, in
   LV_CHECK_ARG(act != 3 || (N % 16 == 0 && bias == nullptr), "lv_gemm_bias_act: fused SwiGLU needs N %% 16 == 0 and no bias");
   if (M == 0) return LV_OK;
   LV_BIND_DEVICE(A);
-  if (M <= 4 && gemv_enabled() && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0)
+  // Weight-stream GEMV for decode-sized M - unless the tensor-core kernel already has a tile for every SM (the LM head:
+  // 594 N-tiles; measured 0.275 ms = 87 % of HBM there against 0.341 ms for the GEMV, round 2)
+  if (M <= 4 && gemv_enabled() && (N + 255) / 256 < sm_count() && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(W) & 15) == 0)
     return launch_gemv(A, W, bias, C, M, N, K, lda, ldw, ldc, act, (cudaStream_t)stream);
   return launch_gemm(A, W, bias, C, M, N, K, lda, ldw, ldc, act, (cudaStream_t)stream);
 }
