@@ -1550,11 +1550,16 @@ extern "C" int lv_attn_cp_fwd(const lv_attn_params* a, const lv_cp_params* c, lv
     return (unsigned long long)(v > 0 ? v : 120000);      // 2 minutes: far beyond any rank skew of a healthy job
   }();
   k.timeout_ns = timeout_ms * 1000000ull;
-  // chunk visiting order: own chunks, then the peers' by ring distance (LV_CP_ORDER=0: plain global order, for A/B runs)
+  // Chunk visiting order.  Default: plain global order - the result is then BIT-IDENTICAL to the single-device kernel
+  // on the gathered K/V (same key order, same rounding sequence), which is what bench.py's in-run parity check
+  // asserts.  LV_CP_ORDER=1: own chunks first, then the peers' by ring distance; measured on 8 GPUs at 18K tokens:
+  // 107.46 ms per prefill against 107.48 ms in global order (the exchange is not what bounds that configuration), and
+  // the output then differs from the single-device kernel by the rounding of a different summation order (3.1e-3
+  // relative between the two bf16 results; both within the test bound against the fp32 oracle).
   k.tiles_per_chunk = (int)(chunk / A_BN);
   static const int ring_order = [] {
     const char* e = getenv("LV_CP_ORDER");
-    return (e != nullptr && e[0] == '0') ? 0 : 1;
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
   }();
   k.order = 0;
   for (int i = 0; i < c->cp; ++i) {
