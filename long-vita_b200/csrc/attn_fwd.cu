@@ -467,7 +467,10 @@ __device__ __forceinline__ WorkItem decode_item(const AttnKParams& p, int item) 
 
 // POLY: every 4th exponential on the FMA pipe (ex2_poly).  TURNS: MUFU turn-taking of the two softmax warps of an
 // SM sub-partition (see the softmax section).  Both are compile-time so the per-step loop carries no flag tests.
-template <int D, bool CP, int POLY, bool TURNS>
+// HALF: the softmax warps publish P in two 64-key halves and the issuer starts the P.V k-steps of the first half while
+// the exponentials of the second half are still running - it takes 256 of the 512 P.V cycles off the serial chain
+// QK -> softmax -> PV of a query tile.
+template <int D, bool CP, int POLY, bool TURNS, bool HALF>
 __global__ void __launch_bounds__(A_THREADS, 1)
     attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -492,7 +495,8 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   uint64_t* o_full = p_full + 2;          // [2]
   uint64_t* o_free = o_full + 2;          // [2]: the epilogue has read O_t out of TMEM (the next item's first P.V overwrites it)
   uint64_t* tok = o_free + 2;             // [2 tiles][4 SM sub-partitions]: MUFU turn-taking, see the softmax warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 8);
+  uint64_t* p_half = tok + 8;             // [2]: the first 64 keys of P_t are in TMEM (HALF: P.V starts on them early)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -511,6 +515,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
       mbar_init(&o_free[i], 4);
+      mbar_init(&p_half[i], 4);
     }
     for (int i = 0; i < 8; ++i) mbar_init(&tok[i], 1);
     for (int i = 0; i < NS; ++i) {
@@ -630,6 +635,11 @@ __global__ void __launch_bounds__(A_THREADS, 1)
         const bool leader = elect_one();
 #pragma unroll
         for (int kk = 0; kk < A_BN / 16; ++kk) {
+          if (HALF && kk == A_BN / 32) {
+            // second half of P_t: pcnt[t] was advanced by the caller, so this step's phase is pcnt[t] - 1
+            mbar_wait(&p_full[t], (pcnt[t] - 1) & 1);
+            tc_fence_after();
+          }
           // A: P_t rows in TMEM, 16 bf16 (= 8 columns) per k-step.  B: V tile, MN-major: 16 key rows
           // (2 KB) per k-step, the second 64 head-dim columns live one 16 KB box further.
           if (leader) umma_ts(tO[t], tS[t] + kk * 8, vd + (uint64_t)(kk * 128), idesc_pv, (accumulate || kk != 0) ? 1u : 0u);
@@ -676,7 +686,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
                 mbar_wait(&v_full[vc % NS], (vc / NS) & 1);
                 ++vcnt_wait;
               }
-              mbar_wait(&p_full[1], pcnt[1] & 1);
+              mbar_wait(HALF ? &p_half[1] : &p_full[1], pcnt[1] & 1);
               ++pcnt[1];
               if (!o_waited[1]) {
                 if (of_cnt[1] > 0) mbar_wait(&o_free[1], (of_cnt[1] - 1) & 1);
@@ -704,7 +714,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
               mbar_wait(&v_full[vc % NS], (vc / NS) & 1);
               ++vcnt_wait;
             }
-            mbar_wait(&p_full[0], pcnt[0] & 1);
+            mbar_wait(HALF ? &p_half[0] : &p_full[0], pcnt[0] & 1);
             ++pcnt[0];
             if (!o_waited[0]) {
               if (of_cnt[0] > 0) mbar_wait(&o_free[0], (of_cnt[0] - 1) & 1);
@@ -736,6 +746,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
     // step going to such scalar set-up on the softmax warps' critical path (profiles/README.md).
     const uint32_t a_sfull = keep_u32(smem_u32(&s_full[t])), a_pfull = keep_u32(smem_u32(&p_full[t]));
     const uint32_t a_ofull = keep_u32(smem_u32(&o_full[t])), a_ofree = keep_u32(smem_u32(&o_free[t]));
+    const uint32_t a_phalf = keep_u32(smem_u32(&p_half[t]));
     // MUFU turn-taking (TURNS): the exponentials of one 128 x 128 score tile keep the MUFU unit of an SM sub-partition
     // busy for ~1050 cycles.  The two softmax warps of a sub-partition (one per query tile) take turns on it - tile
     // 0's warp runs exp(j), then tile 1's exp(j), then tile 0's exp(j+1) ... - so that the load / max / store /
@@ -871,6 +882,12 @@ __global__ void __launch_bounds__(A_THREADS, 1)
             if (give && lane == 0) mbar_arrive_a(a_tok_other);
           }
           tmem_st32(tS + h * 32, pk);
+          if (HALF && h == 0) {
+            tmem_wait_st();          // (also covers the lazy O rescale above)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(a_phalf);
+          }
         }
         l += (l0 + l1) + (l2 + l3);
         tmem_wait_st();
@@ -1352,7 +1369,7 @@ __global__ void __launch_bounds__(A_THREADS, 1)
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int D, bool CP, int VER, int POLY = 0, bool TURNS = false>
+template <int D, bool CP, int VER, int POLY = 0, bool TURNS = false, bool HALF = true>
 static int launch_attn_t(const lv_attn_params* a, const CpKParams* cp, cudaStream_t s) {
   using Cfg = AttnCfg<D>;
   CUtensorMap tmQ, tmK, tmV, tmO;
@@ -1410,7 +1427,7 @@ static int launch_attn_t(const lv_attn_params* a, const CpKParams* cp, cudaStrea
     if constexpr (VER == 2) {
       LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<D, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     } else {
-      LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, CP, POLY, TURNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
+      LV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, CP, POLY, TURNS, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     }
     attr_once.done(attr_dev);
   }
@@ -1424,7 +1441,7 @@ static int launch_attn_t(const lv_attn_params* a, const CpKParams* cp, cudaStrea
   if constexpr (VER == 2)
     attn_fwd2_kernel<D, CP><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p, cpp);
   else
-    attn_fwd_kernel<D, CP, POLY, TURNS><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p, cpp);
+    attn_fwd_kernel<D, CP, POLY, TURNS, HALF><<<grid, A_THREADS, Cfg::SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, p, cpp);
   LV_CHECK_LAUNCH("attn_fwd_kernel");
   return LV_OK;
 }
@@ -1447,14 +1464,19 @@ static int launch_attn(const lv_attn_params* a, const CpKParams* cp, cudaStream_
   } else {
     const bool turns = attn_turns_env() == 1;      // measured round 2: off is faster at both head dims (profiles/README.md)
     const int poly = attn_poly_exp();              // pairs per 8 on the FMA pipe: LV_ATTN_POLY = 0 | 2 | 3 | 4
+    static const int half_env = [] {      // LV_ATTN_HALF=0: whole-tile P hand-off (A/B runs)
+      const char* e = getenv("LV_ATTN_HALF");
+      return (e != nullptr && e[0] == '0') ? 0 : 1;
+    }();
     if constexpr (CP) {     // context-parallel launches: the default only (fewer instantiations of the big kernel)
-      return launch_attn_t<D, CP, 1, ATTN_POLY_DEFAULT, false>(a, cp, s);
+      return launch_attn_t<D, CP, 1, ATTN_POLY_DEFAULT, false, true>(a, cp, s);
     } else {
-      if (turns) return launch_attn_t<D, CP, 1, ATTN_POLY_DEFAULT, true>(a, cp, s);
-      if (poly == 0) return launch_attn_t<D, CP, 1, 0, false>(a, cp, s);
-      if (poly == 2) return launch_attn_t<D, CP, 1, 2, false>(a, cp, s);
-      if (poly == 3) return launch_attn_t<D, CP, 1, 3, false>(a, cp, s);
-      return launch_attn_t<D, CP, 1, 4, false>(a, cp, s);
+      if (turns) return launch_attn_t<D, CP, 1, ATTN_POLY_DEFAULT, true, false>(a, cp, s);
+      if (!half_env) return launch_attn_t<D, CP, 1, ATTN_POLY_DEFAULT, false, false>(a, cp, s);
+      if (poly == 0) return launch_attn_t<D, CP, 1, 0, false, true>(a, cp, s);
+      if (poly == 2) return launch_attn_t<D, CP, 1, 2, false, true>(a, cp, s);
+      if (poly == 3) return launch_attn_t<D, CP, 1, 3, false, true>(a, cp, s);
+      return launch_attn_t<D, CP, 1, 4, false, true>(a, cp, s);
     }
   }
 }
