@@ -505,8 +505,9 @@ static int launch_gemm_t(const void* A, const void* W, const void* bias, void* C
   // M-blocks per rasterisation group: the A panel of a group (gm x 128 rows x K) stays in L2 while its tiles sweep
   // the N-blocks, and W is re-read from HBM once per group, so DRAM traffic ~ A + C + (num_m / gm) * W.  Round 2 ncu
   // inside the bench step, gm = 16: QKV 1107 MB vs 526 MB algorithmic, gate|up 3248 vs 982, down (K = 13824: a 57 MB
-  // panel, A is re-read too) 3096 vs 840.  The group is sized so that the A panel takes ~40 MB of the 126 MB L2
-  // whatever K is (K = 5120 -> 30 M-blocks, K = 13824 -> 11); LV_GEMM_GM forces a value for A/B runs.
+  // panel, A is re-read too) 3096 vs 840.  The group is sized so that the A panel takes ~40 MB of the 126 MB L2 but
+  // never below 16 M-blocks (K = 5120 -> 30: gate|up 3248 -> 2271 MB; K = 13824 -> 16: a group of 11 measured 3462 MB,
+  // worse than 16 - fewer M-blocks per group also means more W passes); LV_GEMM_GM forces a value for A/B runs.
   static const int gm_env = [] {
     const char* e = getenv("LV_GEMM_GM");
     const int v = e ? atoi(e) : 0;
@@ -515,7 +516,7 @@ static int launch_gemm_t(const void* A, const void* W, const void* bias, void* C
   int gm = gm_env;
   if (gm == 0) {
     gm = (int)((40ll << 20) / (256 * K));
-    gm = gm < 8 ? 8 : (gm > 64 ? 64 : gm);
+    gm = gm < 16 ? 16 : (gm > 64 ? 64 : gm);
   }
   gemm_bf16_kernel<G_BN><<<grid, G_THREADS, G_SMEM, s>>>(tmA, tmB, tmC, reinterpret_cast<const __nv_bfloat16*>(bias), (int)M,
                                                          (int)N, (int)K, act, gm);
