@@ -1,4 +1,4 @@
-"""Launch one of each hot-path kernel (for `ncu --set full` capture; see tools/gpu_run7.sh)."""
+"""Launch one of each hot-path kernel (for `ncu --set full -k regex:... python tools/ncu_all.py` captures)."""
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from long_vita_b200 import ops
