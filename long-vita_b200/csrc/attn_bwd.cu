@@ -531,8 +531,8 @@ __global__ void __launch_bounds__(B2_THREADS, 1)
               l2 = p.lse[o] * 1.4426950408889634f;
               dl = p.delta[o];
             }
-            s_lse[st * 128 + c] = l2;
-            s_dlt[st * 128 + c] = dl;
+            s_lse[st * 128 + c] = -l2;      // stored NEGATED: the consumers add them inside packed FFMA2 / FADD2
+            s_dlt[st * 128 + c] = -dl;
           }
           __syncwarp();
         }
@@ -698,25 +698,30 @@ __global__ void __launch_bounds__(B2_THREADS, 1)
           tmem_wait_ld();
           uint32_t pp[16], ds[16];
           if (!masked_tile) {
+            // interior tile: packed fp32 pairs throughout (x = s * scale - lse, dP - delta, p * (dP - delta) * scale: the
+            // same roundings as the scalar forms), column statistics as 8-byte shared-memory loads
 #pragma unroll
             for (int k = 0; k < 32; k += 2) {
               const int c = c2 * 32 + k;
-              float l2a, l2b, dla, dlb;
+              float nl0, nl1, nd0, nd1;
               if (MODE == 0) {
-                l2a = s_lse[st * 128 + b * 64 + c];
-                l2b = s_lse[st * 128 + b * 64 + c + 1];
-                dla = s_dlt[st * 128 + b * 64 + c];
-                dlb = s_dlt[st * 128 + b * 64 + c + 1];
+                const float2 nl = *reinterpret_cast<const float2*>(&s_lse[st * 128 + b * 64 + c]);
+                const float2 nd = *reinterpret_cast<const float2*>(&s_dlt[st * 128 + b * 64 + c]);
+                nl0 = nl.x, nl1 = nl.y, nd0 = nd.x, nd1 = nd.y;
               } else {
-                l2a = l2b = row_lse2;
-                dla = dlb = row_delta;
+                nl0 = nl1 = -row_lse2;
+                nd0 = nd1 = -row_delta;
               }
-              const float p0 = ex2(fmaf(__uint_as_float(sv[k]), sc_log2, -l2a));
-              const float p1 = ex2(fmaf(__uint_as_float(sv[k + 1]), sc_log2, -l2b));
+              float x0, x1;
+              ffma2v(x0, x1, __uint_as_float(sv[k]), __uint_as_float(sv[k + 1]), sc_log2, sc_log2, nl0, nl1);
+              const float p0 = ex2(x0);
+              const float p1 = ex2(x1);
               float d0, d1;
-              fadd2(d0, d1, __uint_as_float(dv[k]), __uint_as_float(dv[k + 1]), -dla, -dlb);
+              fadd2(d0, d1, __uint_as_float(dv[k]), __uint_as_float(dv[k + 1]), nd0, nd1);
+              fmul2(d0, d1, p0, p1, d0, d1);
+              fmul2(d0, d1, d0, d1, sc, sc);
               pp[k / 2] = pack_bf16(p0, p1);
-              ds[k / 2] = pack_bf16(p0 * d0 * sc, p1 * d1 * sc);
+              ds[k / 2] = pack_bf16(d0, d1);
             }
           } else {
 #pragma unroll
@@ -725,12 +730,12 @@ __global__ void __launch_bounds__(B2_THREADS, 1)
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const int c = c2 * 32 + k + e;
-                const float l2 = (MODE == 0) ? s_lse[st * 128 + b * 64 + c] : row_lse2;
-                const float dl = (MODE == 0) ? s_dlt[st * 128 + b * 64 + c] : row_delta;
-                float pe = ex2(fmaf(__uint_as_float(sv[k + e]), sc_log2, -l2));
+                const float nl2 = (MODE == 0) ? s_lse[st * 128 + b * 64 + c] : -row_lse2;
+                const float ndl = (MODE == 0) ? s_dlt[st * 128 + b * 64 + c] : -row_delta;
+                float pe = ex2(fmaf(__uint_as_float(sv[k + e]), sc_log2, nl2));
                 pe = (c >= c_lo && c < c_hi) ? pe : 0.f;
                 pv[e] = pe;
-                dsv[e] = pe * (__uint_as_float(dv[k + e]) - dl) * sc;
+                dsv[e] = pe * (__uint_as_float(dv[k + e]) + ndl) * sc;
               }
               pp[k / 2] = pack_bf16(pv[0], pv[1]);
               ds[k / 2] = pack_bf16(dsv[0], dsv[1]);

@@ -325,6 +325,14 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, 
       : "=f"(d0), "=f"(d1)
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 // Opaque copy: stops the compiler from re-deriving a loop-invariant value inside a hot loop (it re-materialises cheap-
 // looking address arithmetic - S2UR + uniform ALU chains - per iteration to save a register).
 __device__ __forceinline__ uint32_t keep_u32(uint32_t v) {
