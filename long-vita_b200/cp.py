@@ -271,6 +271,8 @@ class CPContext(CPBackwardMixin):
         """Raise (LV_ESTATE) if any attention kernel of this context gave up waiting for a peer rank: every in-kernel
         wait on another GPU is bounded (LV_CP_TIMEOUT_MS), so a dead or diverged peer costs an error here instead of a
         hung node.  Synchronises the current stream - call it where the host reads a result anyway."""
+        if self.base is None:      # closed
+            return
         self._check(self.lib.lv_cp_check_fault(self.fault.data_ptr(), torch.cuda.current_stream().cuda_stream), "lv_cp_check_fault")
 
     def qkv_buffer(self) -> torch.Tensor:

@@ -157,3 +157,69 @@ def test_references_own_sync_output_restores_global_order_from_our_shards():
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(_sync_worker, args=(2, port), nprocs=2, join=True)
+
+
+# ---- key-tile visiting order of the fused exchange kernel (csrc/attn_fwd.cu: KvWalk, cp_copier) ----
+def _order_list(cp, rank, ring):
+    """`k.order` as lv_attn_cp_fwd builds it: 2 cp chunk ids, own chunks first then peers by ring distance (ring) or 0..2cp-1."""
+    out = []
+    for i in range(cp):
+        peer = (rank - i + cp) % cp if ring else i
+        out += [peer, 2 * cp - 1 - peer] if ring else [2 * i, 2 * i + 1]
+    return out
+
+
+def _walk(n0, n1, order, tc):
+    """KvWalk: the tiles [0, lo) both query tiles see first, then [lo, hi), each range in chunk-priority order."""
+    lo, hi = min(n0, n1), max(n0, n1)
+    seq = []
+    for a, b in ((0, lo), (lo, hi)):
+        for ch in order:
+            seq += list(range(max(a, ch * tc), min(b, (ch + 1) * tc)))
+    return seq
+
+
+def _copier_blocks(nb, order, tc):
+    """cp_copier: the i-th staged block in chunk-priority order."""
+    out = []
+    for i in range(nb):
+        j = i
+        for ch in order:
+            cnt = min(max(nb - ch * tc, 0), tc)
+            if j < cnt:
+                out.append(ch * tc + j)
+                break
+            j -= cnt
+    return out
+
+
+def test_visiting_order_model_of_the_exchange_kernel():
+    """A restatement of the kernel's index logic (not the kernel - its parity is tests/test_gpu_cp.py): every key tile a
+    query tile may see is visited exactly once, the shorter query tile takes part in a PREFIX of the steps, the copier
+    stages every needed block once, and in ring order the first blocks are the rank's own."""
+    import random
+
+    rnd = random.Random(0)
+    for cp in (2, 4, 8):
+        for tc in (1, 3, 9):
+            for rank in range(cp):
+                for ring in (False, True):
+                    order = _order_list(cp, rank, ring)
+                    assert sorted(order) == list(range(2 * cp))
+                    nb = (2 * cp - rank) * tc                      # blocks this rank's queries can see
+                    staged = _copier_blocks(nb, order, tc)
+                    assert sorted(staged) == list(range(nb))
+                    if ring:
+                        assert set(staged[:tc]) == set(range(rank * tc, (rank + 1) * tc))     # own first chunk first
+                    else:
+                        assert staged == list(range(nb))
+                    for _ in range(25):
+                        n1 = rnd.randint(0, nb)
+                        n0 = rnd.randint(0, n1)
+                        if rnd.random() < 0.2:
+                            n0, n1 = n1, 0                          # second query tile out of range
+                        seq = _walk(n0, n1, order, tc)
+                        assert sorted(seq) == list(range(max(n0, n1)))
+                        assert sorted(seq[: min(n0, n1)]) == list(range(min(n0, n1)))
+                        if not ring:
+                            assert seq == list(range(max(n0, n1)))  # global order: what the single-device kernel does
