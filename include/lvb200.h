@@ -301,6 +301,20 @@ int lv_frame_preprocess(const void* frames, void* out, void* ws, const int32_t* 
                         const int32_t* coeff, int64_t ksize, int64_t n_frames, int64_t H, int64_t W, int64_t S,
                         const int32_t* background, const float* mean, const float* std, lv_stream_t stream);
 
+/* Dynamic-patch tiling of one image (same survey row): uint8 RGB image [H, W, 3] -> bf16 tiles [*, 3, S, S], bit-identical
+ * to ImageProcessor.process_dynamic (long_vita/data/processor/image_processor.py:263-285) = dynamic_preprocess (:404-448:
+ * PIL BICUBIC resize to out_w x out_h = a grid of S x S tiles chosen by the host, aspect ratio not kept; crop boxes
+ * row-major over the grid) + process_images on the tiles (:211-221) + .to(bfloat16).  The resized pixel (oy, ox) lands in
+ * tile tile_base + (oy / S) * (out_w / S) + ox / S.  The thumbnail tile the reference puts first (:442-447) is a second
+ * call with out_h = out_w = S and tile_base = 0.  x_* / y_* are the resampling tables for W -> out_w and H -> out_h
+ * (device memory, long_vita_b200/preprocess.py::resample_table); mean / std float[3] are HOST arrays; ws is device
+ * workspace of lv_image_tiles_ws_bytes(H, out_w) bytes. */
+int64_t lv_image_tiles_ws_bytes(int64_t H, int64_t out_w);
+int lv_image_tiles_preprocess(const void* image, void* out, void* ws, const int32_t* x_min, const int32_t* x_cnt,
+                              const int32_t* x_coeff, int64_t x_ksize, const int32_t* y_min, const int32_t* y_cnt,
+                              const int32_t* y_coeff, int64_t y_ksize, int64_t H, int64_t W, int64_t out_h, int64_t out_w,
+                              int64_t S, int64_t tile_base, const float* mean, const float* std, lv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

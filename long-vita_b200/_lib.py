@@ -84,6 +84,9 @@ SIGNATURES = {
     "lv_swiglu_bwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr]),
     "lv_frame_preprocess_ws_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64]),
     "lv_frame_preprocess": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "lv_image_tiles_ws_bytes": (c_i64, [c_i64, c_i64]),
+    "lv_image_tiles_preprocess": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64,
+                                          c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
     "lv_ce_accumulate": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr]),
     "lv_ce_grad": (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr]),
     "lv_attn_decode_merge": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr]),

@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "preprocess_core.h"
 
 namespace lv {
 
@@ -95,6 +96,28 @@ __global__ void __launch_bounds__(256) pre_vpass_norm_kernel(const uint8_t* __re
   }
 }
 
+// Dynamic-patch tiling of ONE image (image_processor.py:263-285 process_dynamic, :404-448 dynamic_preprocess): the image
+// is resized to a grid of S x S tiles (out_w x out_h, aspect ratio NOT kept - the host picks the grid) and cut into the
+// tiles; no padding.  Two passes like the frame path, but with separate tables for the two axes; the per-element bodies
+// live in preprocess_core.h (also compiled and tested on the host).
+__global__ void __launch_bounds__(256) pre_resize_h_kernel(const uint8_t* __restrict__ image, uint8_t* __restrict__ tmp,
+                                                           const int* __restrict__ xmin, const int* __restrict__ cnt,
+                                                           const int* __restrict__ kk, int ksize, int H, int W, int OW) {
+  const long long total = (long long)H * OW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    lv_pre_resize_h_item(i, image, tmp, xmin, cnt, kk, ksize, W, OW);
+}
+
+__global__ void __launch_bounds__(256) pre_resize_v_tiles_kernel(const uint8_t* __restrict__ tmp, uint16_t* __restrict__ out,
+                                                                 const int* __restrict__ ymin, const int* __restrict__ cnt,
+                                                                 const int* __restrict__ kk, int ksize, int OH, int OW, int S,
+                                                                 int tile_base, float m0, float m1, float m2, float s0, float s1,
+                                                                 float s2) {
+  const long long total = (long long)OH * OW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    lv_pre_resize_v_tile_item(i, tmp, out, ymin, cnt, kk, ksize, OW, S, tile_base, m0, m1, m2, s0, s1, s2);
+}
+
 }  // namespace lv
 
 using namespace lv;
@@ -132,6 +155,40 @@ extern "C" int lv_frame_preprocess(const void* frames, void* out, void* ws, cons
         reinterpret_cast<const uint8_t*>(ws), reinterpret_cast<__nv_bfloat16*>(out), win_min, win_cnt, coeff, (int)ksize, (int)n_frames, n,
         (int)S, mean[0], mean[1], mean[2], std[0], std[1], std[2]);
     LV_CHECK_LAUNCH("pre_vpass_norm_kernel");
+  }
+  return LV_OK;
+}
+
+extern "C" int64_t lv_image_tiles_ws_bytes(int64_t H, int64_t out_w) { return H * out_w * 3; }
+
+extern "C" int lv_image_tiles_preprocess(const void* image, void* out, void* ws, const int32_t* x_min, const int32_t* x_cnt,
+                                         const int32_t* x_coeff, int64_t x_ksize, const int32_t* y_min, const int32_t* y_cnt,
+                                         const int32_t* y_coeff, int64_t y_ksize, int64_t H, int64_t W, int64_t out_h,
+                                         int64_t out_w, int64_t S, int64_t tile_base, const float* mean, const float* std,
+                                         lv_stream_t stream) {
+  LV_CHECK_ARG(H > 0 && W > 0 && out_h > 0 && out_w > 0 && S > 0 && x_ksize > 0 && y_ksize > 0 && tile_base >= 0,
+               "lv_image_tiles_preprocess: empty shape");
+  LV_CHECK_ARG(H < (1 << 15) && W < (1 << 15) && out_h < (1 << 15) && out_w < (1 << 15), "lv_image_tiles_preprocess: image side too large");
+  LV_CHECK_ARG(out_h % S == 0 && out_w % S == 0, "lv_image_tiles_preprocess: the resized image (%lld x %lld) is not a grid of %lld-pixel tiles",
+               (long long)out_w, (long long)out_h, (long long)S);
+  LV_CHECK_ARG(image && out && ws && x_min && x_cnt && x_coeff && y_min && y_cnt && y_coeff && mean && std,
+               "lv_image_tiles_preprocess: null pointer");
+  LV_BIND_DEVICE(image);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t cap = 32 * (int64_t)sm_count();
+  {
+    const int64_t blocks = (H * out_w + 255) / 256;
+    pre_resize_h_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(
+        reinterpret_cast<const uint8_t*>(image), reinterpret_cast<uint8_t*>(ws), x_min, x_cnt, x_coeff, (int)x_ksize, (int)H, (int)W,
+        (int)out_w);
+    LV_CHECK_LAUNCH("pre_resize_h_kernel");
+  }
+  {
+    const int64_t blocks = (out_h * out_w + 255) / 256;
+    pre_resize_v_tiles_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(
+        reinterpret_cast<const uint8_t*>(ws), reinterpret_cast<uint16_t*>(out), y_min, y_cnt, y_coeff, (int)y_ksize, (int)out_h,
+        (int)out_w, (int)S, (int)tile_base, mean[0], mean[1], mean[2], std[0], std[1], std[2]);
+    LV_CHECK_LAUNCH("pre_resize_v_tiles_kernel");
   }
   return LV_OK;
 }

@@ -7,6 +7,11 @@ exactly as Pillow's `precompute_coeffs` / `normalize_coeffs_8bpc` do (they depen
 target size, so one small table serves every frame of a video) and cached on the device; the pixel work - padding to
 a square with the mean colour, both resampling passes, scaling, normalisation, channel-first bf16 output - runs in
 `lv_frame_preprocess` (csrc/preprocess.cu).
+
+Still images go through the reference's dynamic-patch tiling instead (`ImageProcessor.process_dynamic`,
+image_processor.py:263-285; tools/inference_long_vita.py:643-645): `dynamic_tile_grid` picks the grid of 448-pixel tiles
+(host arithmetic on two integers), `preprocess_image_dynamic` resizes the image to that grid without keeping the aspect
+ratio, cuts it into the tiles and puts a 448 x 448 thumbnail of the whole image first (`lv_image_tiles_preprocess`).
 """
 from __future__ import annotations
 
@@ -92,3 +97,59 @@ def preprocess_frames(frames: torch.Tensor, image_size: int = 448, mean: Sequenc
                                        coeff.data_ptr(), ksize, n, H, W, image_size, bg, m, s,
                                        torch.cuda.current_stream().cuda_stream), "lv_frame_preprocess")
     return out
+
+
+def dynamic_tile_grid(width: int, height: int, min_patch_grid: int = 1, max_patch_grid: int = 12,
+                      image_size: int = 448) -> Tuple[int, int]:
+    """(columns, rows) of the tile grid `dynamic_preprocess` resizes a width x height image to
+    (image_processor.py:404-426 with find_closest_aspect_ratio :387-401): among all grids of min..max tiles the one
+    whose aspect ratio is closest to the image's; on an exact tie a later (larger) grid wins only if the image has more
+    than half its pixels.  Candidates are visited in the reference's order - the iteration order of a `set` of the
+    (i, j) pairs, stably sorted by i * j - because that order decides ties."""
+    aspect = width / height
+    seen = set()
+    for n in range(min_patch_grid, max_patch_grid + 1):
+        for i in range(1, n + 1):
+            for j in range(1, n + 1):
+                if min_patch_grid <= i * j <= max_patch_grid:
+                    seen.add((i, j))
+    best, best_diff = (1, 1), float("inf")
+    for gx, gy in sorted(seen, key=lambda g: g[0] * g[1]):
+        diff = abs(aspect - gx / gy)
+        if diff < best_diff:
+            best, best_diff = (gx, gy), diff
+        elif diff == best_diff and width * height > 0.5 * image_size * image_size * gx * gy:
+            best = (gx, gy)
+    return best
+
+
+def _tiles_call(lib, image, out, H, W, out_h, out_w, S, tile_base, m, s):
+    xt = _device_table(W, out_w, image.device)
+    yt = _device_table(H, out_h, image.device)
+    ws = torch.empty(int(lib.lv_image_tiles_ws_bytes(H, out_w)), dtype=torch.uint8, device=image.device)
+    _lib.check(lib.lv_image_tiles_preprocess(image.data_ptr(), out.data_ptr(), ws.data_ptr(), xt[0].data_ptr(), xt[1].data_ptr(),
+                                             xt[2].data_ptr(), xt[3], yt[0].data_ptr(), yt[1].data_ptr(), yt[2].data_ptr(), yt[3],
+                                             H, W, out_h, out_w, S, tile_base, m, s, torch.cuda.current_stream().cuda_stream),
+               "lv_image_tiles_preprocess")
+
+
+def preprocess_image_dynamic(image: torch.Tensor, min_patch_grid: int = 1, max_patch_grid: int = 12, image_size: int = 448,
+                             mean: Sequence[float] = IMAGENET_DEFAULT_MEAN, std: Sequence[float] = IMAGENET_DEFAULT_STD):
+    """image uint8 [H, W, 3] on the GPU -> (bf16 [n_tiles, 3, image_size, image_size], (grid width, grid height) in pixels)
+    like `ImageProcessor.process_dynamic` (image_processor.py:263-285): n_tiles = columns * rows, plus the thumbnail of
+    the whole image in front when the grid has more than one tile (use_thumbnail=True, :442-447)."""
+    if not (image.is_cuda and image.dtype == torch.uint8 and image.dim() == 3 and image.shape[-1] == 3):
+        raise ValueError("preprocess_image_dynamic expects a CUDA uint8 tensor [H, W, 3]")
+    image = image.contiguous()
+    H, W, _ = image.shape
+    gx, gy = dynamic_tile_grid(W, H, min_patch_grid, max_patch_grid, image_size)
+    S = image_size
+    thumb = 1 if gx * gy > 1 else 0
+    lib = _lib.lib()
+    out = torch.empty((gx * gy + thumb, 3, S, S), dtype=torch.bfloat16, device=image.device)
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    _tiles_call(lib, image, out, H, W, gy * S, gx * S, S, thumb, m, s)
+    if thumb:
+        _tiles_call(lib, image, out, H, W, S, S, S, 0, m, s)
+    return out, (gx * S, gy * S)

@@ -16,6 +16,8 @@ path is integer arithmetic, restated here with numpy:
     (normalize_coeffs_8bpc);
   * horizontal pass over the rows the vertical pass needs, then vertical pass, each accumulating in int32 from
     1 << 21 and clipping (acc >> 22) to [0, 255] - so the intermediate image is uint8 again.
+Dynamic-patch tiling of still images (`process_dynamic` :263-285 = `dynamic_preprocess` :404-448 + `process_images`) is
+restated in `dynamic_grid` / `process_dynamic` below and pinned the same way.
 PINNING: tests/test_oracle_pinning.py runs the reference's own `process_images` (with Pillow) from /root/reference on
 seeded synthetic frames and requires bit-identical float32 output; tests/golden/ref_preprocess.pt carries the same
 frames and outputs for the GPU box.
@@ -104,6 +106,52 @@ def resize_bicubic_u8(img: np.ndarray, out_size: int) -> np.ndarray:
         ym, cn, kk = resample_coeffs(h, out_size)
         cur = _pass(cur, ym, cn, kk, axis=0)
     return cur
+
+
+def resize_bicubic_u8_rect(img: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
+    """PIL `Image.resize((out_w, out_h))` (default filter of Pillow >= 7: BICUBIC) of a uint8 [H, W, 3] image."""
+    h, w, _ = img.shape
+    cur = img
+    if w != out_w:
+        cur = _pass(cur, *resample_coeffs(w, out_w), axis=1)
+    if h != out_h:
+        cur = _pass(cur, *resample_coeffs(h, out_h), axis=0)
+    return cur
+
+
+def dynamic_grid(width: int, height: int, min_num: int = 1, max_num: int = 12, image_size: int = 448) -> Tuple[int, int]:
+    """Tile grid (columns, rows) of `dynamic_preprocess` (image_processor.py:404-426): candidate grids with
+    min_num <= columns * rows <= max_num collected in a set, sorted by tile count (:409-416), and the one closest in
+    aspect ratio chosen by `find_closest_aspect_ratio` (:387-401; ties go to the later candidate when the image area
+    exceeds half the grid's area)."""
+    ratio = width / height
+    cands = sorted({(i, j) for n in range(min_num, max_num + 1) for i in range(1, n + 1) for j in range(1, n + 1)
+                    if min_num <= i * j <= max_num}, key=lambda x: x[0] * x[1])
+    best, best_d = (1, 1), float("inf")
+    area = width * height
+    for c in cands:
+        d = abs(ratio - c[0] / c[1])
+        if d < best_d:
+            best_d, best = d, c
+        elif d == best_d and area > 0.5 * image_size * image_size * c[0] * c[1]:
+            best = c
+    return best
+
+
+def process_dynamic(img: np.ndarray, min_num: int = 1, max_num: int = 12, image_size: int = 448, mean=IMAGENET_DEFAULT_MEAN,
+                    std=IMAGENET_DEFAULT_STD):
+    """uint8 [H, W, 3] image -> (float32 [n, 3, S, S], (grid width, grid height)): process_dynamic (:263-285) - resize to
+    the grid (:424-429), crop the tiles row-major (:431-440), thumbnail of the whole image first if there is more than
+    one tile (:442-447), then process_images on the list (tiles are square and already S x S, so its padding and resize
+    leave them unchanged)."""
+    h, w, _ = img.shape
+    gx, gy = dynamic_grid(w, h, min_num, max_num, image_size)
+    S = image_size
+    big = resize_bicubic_u8_rect(img, gx * S, gy * S)
+    tiles = [big[(i // gx) * S : (i // gx + 1) * S, (i % gx) * S : (i % gx + 1) * S] for i in range(gx * gy)]
+    if len(tiles) != 1:
+        tiles = [resize_bicubic_u8_rect(img, S, S)] + tiles
+    return process_frames(tiles, image_size, mean, std), (gx * S, gy * S)
 
 
 def expand2square(img: np.ndarray, background: Sequence[int]) -> np.ndarray:

@@ -476,3 +476,23 @@ def load_class_methods(rel_path: str, class_name: str, method_names, namespace=N
                     exec(compile(textwrap.dedent(body), f"{path}:{class_name}.{item.name}", "exec"), ns)   # noqa: S102
                     out[item.name] = ns[item.name]
     return out
+
+
+def load_module_functions(rel_path: str, names, namespace=None):
+    """Module-level functions of a reference file, taken by name from its syntax tree like `load_class_methods`
+    (for files whose imports cannot be satisfied here).  Returns {name: function}; the functions share one namespace,
+    so they can call each other."""
+    import ast
+    import textwrap
+
+    path = os.path.join(REF_ROOT, rel_path)
+    src = open(path).read()
+    lines = src.splitlines()
+    ns = dict(namespace or {})
+    out = {}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            body = "\n".join(lines[node.lineno - 1 : node.end_lineno])
+            exec(compile(textwrap.dedent(body), f"{path}:{node.name}", "exec"), ns)   # noqa: S102
+            out[node.name] = ns[node.name]
+    return out

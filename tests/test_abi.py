@@ -110,6 +110,24 @@ def test_backward_and_gemm_argument_errors(lib_built):
     assert h.lv_gemm_bias_act(1, 1, None, 1, 4, 16, 8, 8, 8, 16, 7, None) == -1 and b"unknown activation" in h.lv_last_error()
 
 
+def test_image_tiling_argument_errors(lib_built):
+    import torch
+
+    from long_vita_b200 import _lib
+    from long_vita_b200 import preprocess as PP
+
+    h = _lib.lib()
+    assert h.lv_image_tiles_ws_bytes(300, 896) == 300 * 896 * 3
+    args = lambda oh, ow, base=0: (1, 1, 1, 1, 1, 1, 5, 1, 1, 1, 5, 300, 200, oh, ow, 448, base, 1, 1, None)   # noqa: E731
+    assert h.lv_image_tiles_preprocess(*args(448, 900)) == -1 and b"not a grid of 448-pixel tiles" in h.lv_last_error()
+    assert h.lv_image_tiles_preprocess(*args(0, 448)) == -1 and b"empty shape" in h.lv_last_error()
+    assert h.lv_image_tiles_preprocess(*args(448, 448, -1)) == -1 and b"empty shape" in h.lv_last_error()
+    assert h.lv_image_tiles_preprocess(None, 1, 1, 1, 1, 1, 5, 1, 1, 1, 5, 300, 200, 448, 448, 448, 0, 1, 1, None) == -1
+    assert b"null pointer" in h.lv_last_error()
+    with pytest.raises(ValueError, match="CUDA uint8"):
+        PP.preprocess_image_dynamic(torch.zeros(8, 8, 3, dtype=torch.uint8))
+
+
 def test_missing_extension_fails_loudly(monkeypatch):
     """No CPU / PyTorch fallback: without liblvb200.so every operator raises, naming the build command."""
     from long_vita_b200 import _lib

@@ -437,3 +437,39 @@ def test_frame_preprocessing_oracle_matches_the_reference_live_at_448():
         xm, cn, kk = P.resample_coeffs(a, 448)
         x2, c2, r2, _ = PP.resample_table(a, 448)
         assert np.array_equal(xm, np.array(x2)) and np.array_equal(cn, np.array(c2)) and np.array_equal(kk, np.array(r2))
+
+
+def test_dynamic_tiling_oracle_matches_the_references_own_process_dynamic_fixture():
+    """tests/golden/ref_preprocess_dynamic.pt = outputs of the reference's own ImageProcessor.process_dynamic
+    (image_processor.py:263-285 with dynamic_preprocess :404-448, Pillow's resize) on seeded images at a 28-pixel tile
+    (wide, tall, square, tiny; up- and down-scaled; 1 to 12 tiles + thumbnail) - tests/golden/make_golden.py."""
+    import numpy as np
+
+    from oracle import preprocess as P
+
+    g = torch.load(os.path.join(GOLD, "ref_preprocess_dynamic.pt"))
+    for im, ref, gp in zip(g["images"], g["out"], g["grid_pixels"]):
+        got, grid = P.process_dynamic(im.numpy(), g["min_patch_grid"], g["max_patch_grid"], g["image_size"])
+        assert grid == tuple(gp)
+        assert np.array_equal(got, ref.numpy()), tuple(im.shape)
+
+
+def test_dynamic_tiling_oracle_matches_the_reference_live_at_448():
+    """The same comparison live, at the real tile size, including a grid that is narrower than the image on one axis
+    and wider on the other."""
+    if not ref_loader.available():
+        pytest.skip("/root/reference is not mounted")
+    import numpy as np
+
+    sys.path.insert(0, GOLD)
+    from make_golden import reference_process_dynamic
+
+    from oracle import preprocess as P
+
+    rng = np.random.default_rng(5)
+    for h, w in ((500, 700), (1300, 400), (448, 448), (600, 2100)):
+        im = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref, gref = reference_process_dynamic(im, 448)
+        got, grid = P.process_dynamic(im, 1, 12, 448)
+        assert grid == tuple(int(x) for x in gref), (h, w)
+        assert np.array_equal(got, ref.numpy()), (h, w)
