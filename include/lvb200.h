@@ -88,7 +88,7 @@ int lv_attn_fwd(const lv_attn_params* p, lv_stream_t stream);
  * pretrain_long_vita.py.  `fwd` repeats the forward call's arguments with `out` and `lse` holding the
  * forward results (lse is required).  d_out has the layout of out; dq / dk / dv have the shapes of
  * q / k / v (GQA: dk, dv are summed over the query heads of each group).  delta_ws is caller
- * workspace of batch*hq*sq floats.  Deterministic (no atomics): two tensor-core passes, one for
+ * workspace of lv_attn_bwd_ws_bytes(batch, hq, sq) bytes (batch*hq*sq floats).  Deterministic (no atomics): two tensor-core passes, one for
  * dK/dV and one for dQ.
  * ------------------------------------------------------------------------------------------ */
 typedef struct lv_attn_bwd_params {
@@ -104,6 +104,7 @@ typedef struct lv_attn_bwd_params {
   float* delta_ws;        /* float [b, hq, sq] */
 } lv_attn_bwd_params;
 
+int64_t lv_attn_bwd_ws_bytes(int64_t batch, int64_t hq, int64_t sq);
 int lv_attn_bwd(const lv_attn_bwd_params* p, lv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

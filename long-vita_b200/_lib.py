@@ -60,6 +60,7 @@ SIGNATURES = {
     "lv_last_error": (C.c_char_p, []),
     "lv_launch_count": (c_i64, []),
     "lv_attn_fwd": (c_i32, [C.POINTER(AttnParams), c_ptr]),
+    "lv_attn_bwd_ws_bytes": (c_i64, [c_i64, c_i64, c_i64]),
     "lv_attn_bwd": (c_i32, [C.POINTER(AttnBwdParams), c_ptr]),
     "lv_attn_cp_fwd": (c_i32, [C.POINTER(AttnParams), C.POINTER(CpParams), c_ptr]),
     "lv_cp_check_fault": (c_i32, [c_ptr, c_ptr]),

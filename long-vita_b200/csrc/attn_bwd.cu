@@ -896,6 +896,8 @@ static int launch_bwd(const lv_attn_bwd_params* a, cudaStream_t s) {
 
 using namespace lv;
 
+extern "C" int64_t lv_attn_bwd_ws_bytes(int64_t batch, int64_t hq, int64_t sq) { return batch * hq * sq * (int64_t)sizeof(float); }
+
 extern "C" int lv_attn_bwd(const lv_attn_bwd_params* a, lv_stream_t stream) {
   LV_CHECK_ARG(a != nullptr, "lv_attn_bwd: null params");
   const lv_attn_params* f = &a->fwd;

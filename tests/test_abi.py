@@ -104,6 +104,7 @@ def test_backward_and_gemm_argument_errors(lib_built):
     from long_vita_b200._lib import AttnBwdParams
 
     h = _lib.lib()
+    assert h.lv_attn_bwd_ws_bytes(1, 40, 16384) == 40 * 16384 * 4
     b = AttnBwdParams()
     assert h.lv_attn_bwd(ctypes.byref(b), None) == -1 and b"required" in h.lv_last_error()
     assert h.lv_gemm_bias_act(1, 1, None, 1, 4, 24, 8, 8, 8, 24, 3, None) == -1 and b"SwiGLU" in h.lv_last_error()
