@@ -216,6 +216,23 @@ def test_model_is_a_module_with_the_reference_state_dict(setup):
         assert sd[k_].shape == t.shape and torch.equal(sd[k_], t), k_
 
 
+def test_module_movement_reaches_the_plain_weight_tensors(setup):
+    """`.to()` / `.cuda()` go through nn.Module._apply; the weights are plain (fused) tensors, not Parameters, so the
+    holder classes forward the conversion to every tensor they keep - and nothing is shared with the original."""
+    import copy
+
+    cfg, w, model, _ = setup
+    m2 = copy.deepcopy(model).to(torch.float64)
+    assert m2.dtype == torch.float64 and m2.model.embed_tokens.dtype == torch.float64
+    assert m2.model.layers[0].wqkv.dtype == torch.float64 and m2.model.inv_freq.dtype == torch.float64
+    sd2 = m2.state_dict()
+    assert set(sd2) == set(w)
+    for k_, t in w.items():
+        assert sd2[k_].dtype == torch.float64 and torch.equal(sd2[k_], t.double()), k_
+    assert model.dtype == torch.bfloat16 and model.model.layers[0].wqkv.dtype == torch.bfloat16      # the original is untouched
+    assert list(model.parameters()) == []          # nothing for an optimizer to pick up by accident
+
+
 def test_from_pretrained_reads_an_hf_checkpoint_directory(setup, tmp_path):
     import dataclasses
     import json

@@ -494,6 +494,28 @@ def test_forward_glue_equals_the_references_own_gptvl_forward(tiny, model):
                     got = model(ids, pos, None, **kw)
                     model.fused_loss = True
                 assert got.shape == want.shape and torch.equal(got, want), sorted(kw)
+            # the switches of the training tail (:352-369, :393-395): instruction-dataset shift, logit scale, soft-capping
+            for variant in (dict(is_instruction_dataset=True), dict(output_multiplier_scale=0.5),
+                            dict(output_logit_softcapping=30.0),
+                            dict(is_instruction_dataset=True, output_multiplier_scale=2.0, output_logit_softcapping=20.0)):
+                for k_, v_ in variant.items():
+                    setattr(args, k_, v_)
+                    setattr(model, k_, v_)
+                try:
+                    for kw in (dict(external_inputs=ext, logit_mask=mask, labels=labels), dict(external_inputs=ext, logit_mask=mask)):
+                        want = ref_forward(me, ids, pos, None, **kw)
+                        got = model(ids, pos, None, **kw)
+                        assert got.shape == want.shape, (variant, sorted(kw))
+                        if "labels" in kw and set(variant) == {"is_instruction_dataset"}:      # the fused tail takes this one
+                            assert torch.allclose(got, want, rtol=1e-6, atol=1e-5), variant
+                            model.fused_loss = False
+                            got = model(ids, pos, None, **kw)
+                            model.fused_loss = True
+                        assert torch.equal(got, want), (variant, sorted(kw))
+                finally:
+                    for k_ in variant:
+                        setattr(args, k_, False if k_ == "is_instruction_dataset" else None)
+                        setattr(model, k_, False if k_ == "is_instruction_dataset" else None)
     finally:
         dist.destroy_process_group()
 

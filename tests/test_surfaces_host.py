@@ -44,6 +44,29 @@ def test_core_attention_slot_conventions():
         B200DotProductAttention(stub.TransformerConfig(attention_dropout=0.1), 1, stub.AttnMaskType.causal)
 
 
+def test_core_attention_slot_training_branch_returns_gradients_in_megatron_layout():
+    """With gradients enabled the slot takes the differentiable path (lv_attn_bwd behind ops.attention): dq / dk / dv
+    must come back in Megatron's [s, b, heads, hn] layout through the permutes around the kernel call, GQA-summed."""
+    from long_vita_b200.megatron.core_attention import B200DotProductAttention
+
+    cfg = stub.TransformerConfig(hidden_size=256, num_attention_heads=8, num_query_groups=2)
+    attn = B200DotProductAttention(cfg, 1, stub.AttnMaskType.causal)
+    q, k, v = (t.requires_grad_(True) for t in _qkv_sbhd(80, 2, 8, 2, 32, 5))
+    d_out = randn_bf16((80, 2, 256), seeded(6))
+    with oracle_ops():
+        out = attn(q, k, v, None)
+        assert out.requires_grad and out.shape == (80, 2, 256)
+        out.backward(d_out)
+    qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    ref, _ = O.attention(qf.permute(1, 0, 2, 3), kf.permute(1, 0, 2, 3), vf.permute(1, 0, 2, 3), causal=True)
+    ref.permute(1, 0, 2, 3).reshape(80, 2, 256).backward(d_out.float())
+    assert rel_fro(out, ref.permute(1, 0, 2, 3).reshape(80, 2, 256)) < 5e-3
+    for got, want, name in ((q.grad, qf.grad, "dq"), (k.grad, kf.grad, "dk"), (v.grad, vf.grad, "dv")):
+        assert got.shape == want.shape and rel_fro(got, want) < 1e-2, name
+    with oracle_ops(), torch.no_grad():                 # inference: the plain forward, no graph
+        assert not attn(q, k, v, None).requires_grad
+
+
 def test_patch_registry_wrapper_semantics():
     """patch_utils.py:46-53: a function named *wrapper decorates the original attribute.  bf16 CUDA inputs
     take the fused path; anything else falls through to the original eager forward (here: the stub's, which
