@@ -130,7 +130,7 @@ def _patch_embed(images, w_pad, bias, cls, pos, patch):
     pe = F.conv2d(images.float(), w.float(), None if bias is None else bias.float(), stride=patch).flatten(2).transpose(1, 2)
     if cls is not None:
         pe = torch.cat([cls.float().reshape(1, 1, -1).expand(pe.shape[0], 1, -1), pe], dim=1)
-    return _bf(pe + pos.float().reshape(1, -1, C))
+    return _bf(pe + pos.float().reshape(1, -1, C)).contiguous()      # the kernel writes a fresh contiguous [n, S, C]
 
 
 def _row_scatter_zero(x, idx, n_rows_out):

@@ -278,3 +278,36 @@ def test_generate_follows_the_inference_script_contract(setup):
     with pytest.raises(NotImplementedError):
         model.generate(inputs=ids, do_sample=True)
     model.generation_config.max_new_tokens = 1024
+
+
+def test_siglip_tower_composition_head_dim_72_padding_and_interleaved_qkv():
+    """a9 host logic (the GPU twin is tests/test_gpu_model.py::test_siglip_tower_matches_oracle): Megatron's per-head
+    interleaved linear_qkv rows, the zero padding of head_dim 72 to the kernel's 128 with scale 72^-0.5, no class token,
+    tanh-GELU - composed from the operator wrappers, against oracle.model.siglip_forward (pinned to transformers'
+    SiglipVisionModel in tests/test_oracle_pinning.py)."""
+    from long_vita_b200.hf.siglip import SigLIPConfig, SigLIPViTModel
+
+    cfg = SigLIPConfig(hidden_size=144, ffn_hidden_size=304, num_layers=2, num_attention_heads=2, kv_channels=72, image_size=112)
+    g = torch.Generator().manual_seed(21)
+
+    def rn(*shape, std=0.05):
+        return (torch.randn(*shape, generator=g) * std).to(torch.bfloat16)
+
+    C, I = cfg.hidden_size, cfg.ffn_hidden_size
+    w = {"conv1.weight": rn(C, 3, 14, 14), "conv1.bias": rn(C), "position_embeddings.weight": rn(cfg.num_patches, C, std=1.0)}
+    for i in range(cfg.num_layers):
+        p = f"decoder.layers.{i}."
+        w.update({
+            p + "input_layernorm.weight": (1 + rn(C)).to(torch.bfloat16), p + "input_layernorm.bias": rn(C),
+            p + "self_attention.linear_qkv.weight": rn(3 * C, C), p + "self_attention.linear_qkv.bias": rn(3 * C),
+            p + "self_attention.linear_proj.weight": rn(C, C), p + "self_attention.linear_proj.bias": rn(C),
+            p + "pre_mlp_layernorm.weight": (1 + rn(C)).to(torch.bfloat16), p + "pre_mlp_layernorm.bias": rn(C),
+            p + "mlp.linear_fc1.weight": rn(I, C), p + "mlp.linear_fc1.bias": rn(I),
+            p + "mlp.linear_fc2.weight": rn(C, I), p + "mlp.linear_fc2.bias": rn(C),
+        })
+    images = torch.randn(2, 3, 112, 112, generator=g).to(torch.bfloat16)
+    with oracle_ops():
+        out = SigLIPViTModel(cfg, w)(images)
+    ref = OM.siglip_forward(cfg, OM.cast_weights(w, torch.float32), images.float())
+    assert out.shape == (2, 64, C)
+    assert rel_fro(out, ref) < 6e-3, rel_fro(out, ref)
