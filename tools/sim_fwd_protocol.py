@@ -14,9 +14,11 @@ covers what the barriers are there for - an operand being overwritten while a qu
 
 Barriers follow mbarrier semantics: `arrive` decrements the pending count of the current phase, completing it (and
 re-arming the count) at zero; `wait(parity)` passes iff the current phase parity differs from `parity` - so a waiter
-two phases behind blocks forever (the deadlock of the first multi-item run at head_dim 64 in round 2: the issuer
-counted an o_free phase for every item while the epilogue warps arrive on it only in items where their query tile has
-key tiles - the ViT's last query block has an empty second tile).  The scheduler picks runnable actors at random; a
+two phases behind blocks forever.  That is the deadlock of the first multi-item run at head_dim 64 in round 2
+(`round2_bug=True` restores that version): o_free completed a phase in EVERY item, and for a query tile without key
+tiles - the ViT's last query block has an empty second tile - the issuer consumed the phase at the END of the item, by
+which time the tile's epilogue warps (which wait for nothing but the Q load) could already have arrived for the
+current item as well.  The scheduler picks runnable actors at random; a
 run fails on deadlock or on any of the operand checks.  `skip` removes single waits, to show that each one is needed
 and that the checks see its absence (tests/test_protocol_sim.py).  One is not: the o_free wait is implied by p_half -
 the warps that read O_t out in the epilogue are the ones that write the next item's first P_t, so the first PV of the
@@ -47,7 +49,8 @@ class Sim:
     """items: list of (n0, n1) = key tiles visible to the two 128-row query tiles of each work item of this CTA.
     NS: K / V ring stages (2 at head_dim 128, 4 at 64).  QB: Q buffers per query tile (LV_ATTN_QBUF64)."""
 
-    def __init__(self, items, seed, NS=2, QB=1, skip=()):
+    def __init__(self, items, seed, NS=2, QB=1, skip=(), round2_bug=False):
+        self.round2_bug = round2_bug
         self.rng = random.Random(seed)
         self.items, self.NS, self.QB = items, NS, QB
         self.skip = set(skip)        # waits left out on purpose: o_free | p_full | p_half | k_empty | v_empty | q_empty | o_full
@@ -177,7 +180,7 @@ class Sim:
             qb, qpar = item_cnt % QB, (item_cnt // QB) & 1
             yield ("wait", f"q_full{qb * 2 + 0}", qpar)
             yield ("wait", f"q_full{qb * 2 + 1}", qpar)
-            o_waited = [False, False]
+            o_waited = [False, False] if not self.round2_bug else [item_cnt == 0, item_cnt == 0]
             vbase = vcnt_wait
             for j in range(nmax + 1):
                 kst = 0
@@ -197,7 +200,9 @@ class Sim:
                             yield ("wait", "p_half1", pcnt[1] & 1)
                         pcnt[1] += 1
                         if not o_waited[1]:
-                            if of_cnt[1] > 0 and "o_free" not in self.skip:
+                            if self.round2_bug:
+                                yield ("wait", "o_free1", (item_cnt - 1) & 1)
+                            elif of_cnt[1] > 0 and "o_free" not in self.skip:
                                 yield ("wait", "o_free1", (of_cnt[1] - 1) & 1)
                             o_waited[1] = True
                         yield from issue_pv(1, item_cnt, j - 1, vc % NS, j - 1 > 0)
@@ -220,18 +225,24 @@ class Sim:
                         yield ("wait", "p_half0", pcnt[0] & 1)
                     pcnt[0] += 1
                     if not o_waited[0]:
-                        if of_cnt[0] > 0 and "o_free" not in self.skip:
+                        if self.round2_bug:
+                            yield ("wait", "o_free0", (item_cnt - 1) & 1)
+                        elif of_cnt[0] > 0 and "o_free" not in self.skip:
                             yield ("wait", "o_free0", (of_cnt[0] - 1) & 1)
                         o_waited[0] = True
                     yield from issue_pv(0, item_cnt, j, vc % NS, j > 0)
                     if j == n0 - 1:
                         self.pipe.append(("commit", "o_full0"))
+            if self.round2_bug:      # "a tile without key tiles issued no P.V: consume its o_free phase all the same"
+                for t in range(2):
+                    if not o_waited[t]:
+                        yield ("wait", f"o_free{t}", (item_cnt - 1) & 1)
             c0, c1 = self.of_counts(n0, n1)
             of_cnt[0] += int(c0)
             of_cnt[1] += int(c1)
 
     def softmax_arrives_o_free(self, n):
-        return n > 0
+        return n > 0 or self.round2_bug
 
     def softmax_warp(self, t, quad):
         QB = self.QB
