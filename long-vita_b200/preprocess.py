@@ -19,6 +19,7 @@ import ctypes as C
 import math
 from typing import Dict, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -30,49 +31,44 @@ _PRECISION_BITS = 32 - 8 - 2
 _tables: Dict[Tuple[int, int, str], Tuple[torch.Tensor, torch.Tensor, torch.Tensor, int]] = {}
 
 
-def _bicubic(x: float) -> float:
-    a = -0.5
-    x = abs(x)
-    if x < 1.0:
-        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
-    if x < 2.0:
-        return (((x - 5) * x + 8) * x - 4) * a
-    return 0.0
-
-
 def resample_table(in_size: int, out_size: int):
     """Windows and 22-bit fixed-point weights of PIL's BICUBIC resize from `in_size` to `out_size` pixels
-    (Resample.c precompute_coeffs + normalize_coeffs_8bpc).  Returns python lists (xmin, count, coeff rows, ksize)."""
+    (Resample.c precompute_coeffs + normalize_coeffs_8bpc).  Returns (xmin int32 [out], count int32 [out],
+    coeff int32 [out, ksize], ksize).  Vectorised over the output coordinates in float64 with Pillow's operation order
+    per element - the window sum runs left to right, one column at a time - so the table is bit-identical to Pillow's
+    (tests/test_oracle_pinning.py, tests/test_preprocess_tiles_host.py); a still image needs four such tables, which a
+    per-pixel Python loop made slower than the GPU work itself."""
     scale = in_size / out_size
     filterscale = max(scale, 1.0)
     support = 2.0 * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
     ss = 1.0 / filterscale
-    xmin, cnt, rows = [], [], []
+    center = (np.arange(out_size, dtype=np.float64) + 0.5) * scale
+    lo = np.maximum(np.trunc(center - support + 0.5).astype(np.int64), 0)        # C's (int) cast truncates toward zero
+    hi = np.minimum(np.trunc(center + support + 0.5).astype(np.int64), in_size)
+    cnt = hi - lo
+    x = np.arange(ksize, dtype=np.int64)[None, :]
+    valid = x < cnt[:, None]
+    t = np.abs(((x + lo[:, None]).astype(np.float64) - center[:, None] + 0.5) * ss)
+    a = -0.5
+    w = np.where(t < 1.0, ((a + 2.0) * t - (a + 3.0)) * t * t + 1, np.where(t < 2.0, (((t - 5) * t + 8) * t - 4) * a, 0.0))
+    w = np.where(valid, w, 0.0)
+    ww = np.zeros(out_size, np.float64)
+    for c in range(ksize):                     # Pillow accumulates the window sum in this order
+        ww = np.where(valid[:, c], ww + w[:, c], ww)
+    nz = ww != 0.0
+    w = np.where(nz[:, None], w / np.where(nz, ww, 1.0)[:, None], w)
     one = float(1 << _PRECISION_BITS)
-    for xx in range(out_size):
-        center = (xx + 0.5) * scale
-        lo = max(int(center - support + 0.5), 0)
-        hi = min(int(center + support + 0.5), in_size)
-        w = [_bicubic((x + lo - center + 0.5) * ss) for x in range(hi - lo)]
-        ww = 0.0
-        for v in w:
-            ww += v
-        if ww != 0.0:
-            w = [v / ww for v in w]
-        row = [int(v * one - 0.5) if v < 0 else int(v * one + 0.5) for v in w]
-        rows.append(row + [0] * (ksize - len(row)))
-        xmin.append(lo)
-        cnt.append(hi - lo)
-    return xmin, cnt, rows, ksize
+    fixed = np.where(w < 0, np.trunc(w * one - 0.5), np.trunc(w * one + 0.5))
+    rows = np.where(valid, fixed, 0.0).astype(np.int32)
+    return lo.astype(np.int32), cnt.astype(np.int32), np.ascontiguousarray(rows), ksize
 
 
 def _device_table(in_size: int, out_size: int, device):
     key = (in_size, out_size, str(device))
     if key not in _tables:
         xmin, cnt, rows, ksize = resample_table(in_size, out_size)
-        _tables[key] = (torch.tensor(xmin, dtype=torch.int32, device=device), torch.tensor(cnt, dtype=torch.int32, device=device),
-                        torch.tensor(rows, dtype=torch.int32, device=device).contiguous(), ksize)
+        _tables[key] = (torch.from_numpy(xmin).to(device), torch.from_numpy(cnt).to(device), torch.from_numpy(rows).to(device), ksize)
         if len(_tables) > 16:
             _tables.pop(next(iter(_tables)))
     return _tables[key]

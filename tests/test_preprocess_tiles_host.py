@@ -55,6 +55,19 @@ def test_tile_grid_equals_the_references_own_dynamic_preprocess():
         assert PP.dynamic_tile_grid(w, h, 1, 6, 336) == reference_dynamic_grid(w, h, 336, 1, 6), (w, h)
 
 
+def test_vectorised_resampling_tables_equal_the_oracle_loop():
+    """long_vita_b200.preprocess.resample_table (numpy, one column of the window at a time) against the oracle's
+    per-pixel restatement of Pillow's precompute_coeffs / normalize_coeffs_8bpc: windows and 22-bit weights identical."""
+    rng = np.random.default_rng(0)
+    pairs = [(1920, 448), (448, 448), (448, 1792), (3840, 1792), (2160, 896), (1, 28), (5, 3), (3, 5), (5376, 448), (448, 5376),
+             (1000, 999), (999, 1000)] + [(int(a), int(b)) for a, b in rng.integers(1, 2500, (60, 2))]
+    for a, b in pairs:
+        xm, cn, kk = OP.resample_coeffs(a, b)
+        x2, c2, r2, k2 = PP.resample_table(a, b)
+        assert kk.shape[1] == k2 and x2.dtype == c2.dtype == r2.dtype == np.int32, (a, b)
+        assert np.array_equal(xm, x2) and np.array_equal(cn, c2) and np.array_equal(kk, r2), (a, b)
+
+
 @pytest.fixture(scope="module")
 def host_kernels(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("pre_host") / "libpre_tiles_host.so")
