@@ -223,3 +223,32 @@ def test_visiting_order_model_of_the_exchange_kernel():
                         assert sorted(seq[: min(n0, n1)]) == list(range(min(n0, n1)))
                         if not ring:
                             assert seq == list(range(max(n0, n1)))  # global order: what the single-device kernel does
+
+
+def test_shared_context_cache_is_bounded_and_evicts_least_recently_used():
+    """CPContext.shared keeps at most MAX_SHARED geometries alive and closes the least recently used one (every rank makes
+    the same calls in the same order, so the collective close() lines up).  The peer-mapped buffers need GPUs, so the
+    bookkeeping is exercised on a subclass whose constructor / close only record what happened."""
+    from long_vita_b200.cp import CPContext
+
+    events = []
+
+    class Fake(CPContext):
+        _shared = {}
+
+        def __init__(self, group, seq_total, hq, hkv, d, device, fused_qkv=True):
+            self.S = seq_total
+            events.append(("open", seq_total))
+
+        def close(self):
+            events.append(("close", self.S))
+
+    a = Fake.shared(None, 1024, 8, 2, 64, "cpu")
+    b = Fake.shared(None, 2048, 8, 2, 64, "cpu")
+    assert Fake.shared(None, 1024, 8, 2, 64, "cpu") is a            # hit: no new buffers, 1024 becomes most recent
+    c = Fake.shared(None, 4096, 8, 2, 64, "cpu")                      # third geometry: evicts 2048, not 1024
+    assert events == [("open", 1024), ("open", 2048), ("close", 2048), ("open", 4096)]      # closed BEFORE the new one opens
+    assert Fake.shared(None, 1024, 8, 2, 64, "cpu") is a and Fake.shared(None, 4096, 8, 2, 64, "cpu") is c
+    assert len(Fake._shared) == Fake.MAX_SHARED == 2
+    assert Fake.shared(None, 2048, 8, 2, 64, "cpu") is not b        # was closed: a fresh context
+    assert Fake.shared(None, 1024, 8, 2, 64, "cpu", fused_qkv=False) is not a     # the layout is part of the key
